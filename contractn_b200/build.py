@@ -1,0 +1,59 @@
+"""Build the CUDA shared library in-tree (sm_100a only).
+
+``python -m contractn_b200.build`` or ``__graft_entry__.build()``.  nvcc
+cross-compiles without a GPU; the resulting ``libctn_b200.so`` is git-ignored
+but travels to the GPU box with the repository snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libctn_b200.so")
+SOURCES = ["plan.cu", "kernels.cu", "gemm.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
+    "-shared",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    built = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(ROOT, "include", "ctn_b200.h"))
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu into contractn_b200/libctn_b200.so.  Returns its path."""
+    if not force and not _stale():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    os.replace(LIB + ".tmp", LIB)
+    if verbose:
+        print(proc.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,160 @@
+// Internal structures shared by the plan compiler (host) and the kernels.
+// Not part of the ABI; see include/ctn_b200.h for the public surface.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "ctn_b200.h"
+
+namespace ctn {
+
+constexpr int kMaxIn = 8;          // inputs of one generic step
+constexpr int kChainMaxIn = 512;   // inputs of one fused Hadamard-chain launch
+constexpr int kMaxPartials = 148 * 16;  // upper bound on the grid of any reducing kernel
+constexpr double kMinNorm = 1e-7;  // contractn/einsum.py:94
+
+// launch kinds (ctn_plan_launch_kind)
+enum LaunchKind : int32_t {
+  kGeneric = 0,
+  kChain = 1,
+  kInterp = 2,
+  kGemm = 3,
+  kFinalize = 4,
+  kMaterialize = 5,  // second pass of a tracked Hadamard chain
+};
+
+// One loop index of a step: extent and element stride in every input.
+// Output strides are implicit: the output is C-contiguous over the out modes.
+struct ModeDev {
+  int64_t extent;
+  int64_t stride[kMaxIn];
+};
+
+// GEMM view of a pairwise step: four groups of modes with strides into A, B, C.
+struct GemmMode {
+  int64_t extent;
+  int64_t sa, sb, sc;
+};
+constexpr int kGemmMaxModes = 12;  // per group, after fusion
+
+struct GemmDev {
+  int32_t n_batch, n_m, n_n, n_k;
+  GemmMode batch[kGemmMaxModes];
+  GemmMode m[kGemmMaxModes];
+  GemmMode n[kGemmMaxModes];
+  GemmMode k[kGemmMaxModes];
+  int64_t B, M, N, K;
+};
+
+// Device-side description of one step.
+struct StepDev {
+  int32_t kind;        // LaunchKind of the kernel that runs it
+  int32_t n_in;
+  int32_t in_slot[kMaxIn];  // generic / gemm steps
+  int32_t slot_off;    // chain steps: offset into the plan's slot list
+  int32_t out_slot;
+  int32_t n_out_modes; // generic: the first n_out_modes modes index the output
+  int32_t n_k_modes;   //          followed by n_k_modes summed modes
+  int32_t mode_off;    // offset into the plan's mode table
+  int32_t gemm_off;    // index into the plan's GemmDev table (-1 = none)
+  int32_t ticket;      // index of this step's arrival counter
+  int32_t is_final;    // output of the whole plan
+  int32_t tracked;     // chain: per-element exponent tracking (n_in > 2)
+  int64_t scratch_off; // chain: byte offset of the per-tile exponent array in the arena
+  int64_t out_numel;
+  int64_t k_numel;
+};
+
+// Per-execution mutable state, at the start of the caller's workspace.
+struct StateHdr {
+  double log_scale;   // contractn/einsum.py:338
+  int32_t flags;      // CTN_RESULT_*
+  int32_t chain_exp;  // global exponent of the last tracked chain
+  double chain_mean;  // its mean |value| relative to 2^chain_exp
+  double reserved;
+};
+
+struct StateLayout {
+  size_t hdr = 0;          // StateHdr
+  size_t inv_kappa = 0;    // double[n_slots]   pending 1/kappa per tensor
+  size_t kappa = 0;        // double[n_slots]
+  size_t tickets = 0;      // uint32[n_tickets]
+  size_t partials = 0;     // double[4 * kMaxPartials]
+  size_t partial_exp = 0;  // int32[2 * kMaxPartials]
+  size_t ptrs = 0;         // void*[n_slots]
+  size_t init_bytes = 0;   // [0, init_bytes) is (re)initialised by every execute
+  size_t total = 0;        // start of the intermediates arena
+};
+
+struct Slot {
+  std::vector<int32_t> labels;
+  std::vector<int64_t> extents;
+  std::vector<int64_t> strides;  // elements
+  int64_t numel = 1;
+  int32_t operand = -1;    // >= 0: caller operand index
+  int64_t ws_offset = -1;  // >= 0: byte offset inside the intermediates arena
+  bool is_final = false;
+};
+
+struct Launch {
+  int32_t kind;
+  int32_t first_step, last_step;  // inclusive range of StepDev entries
+  int64_t bytes;                  // algorithmic bytes moved by this launch
+  double flops;
+};
+
+struct Plan {
+  int32_t dtype = CTN_F64;
+  int32_t flags = 0;
+  int32_t n_operands = 0;
+  size_t elem = 8;
+  std::vector<Slot> slots;
+  std::vector<StepDev> steps;
+  std::vector<ModeDev> modes;
+  std::vector<GemmDev> gemms;
+  std::vector<int32_t> slot_list;  // chain inputs
+  std::vector<Launch> launches;
+  int32_t final_slot = -1;
+  int32_t n_tickets = 0;
+  double flops = 0;
+  StateLayout state;
+  size_t arena_bytes = 0;
+  // device copies (immutable after create)
+  StepDev* d_steps = nullptr;
+  ModeDev* d_modes = nullptr;
+  GemmDev* d_gemms = nullptr;
+  int32_t* d_slot_list = nullptr;
+  int device = 0;
+  int sm_count = 148;
+  // host-buffer path scratch (ctn_plan_execute_host)
+  void* h_ws = nullptr;
+  size_t h_ws_bytes = 0;
+  std::vector<void*> h_operands;
+  std::vector<size_t> h_operand_bytes;
+  void* h_out = nullptr;
+  double* h_log = nullptr;
+};
+
+// kernels.cu
+struct ExecCtx {
+  const Plan* plan;
+  char* ws;             // workspace base (device)
+  cudaStream_t stream;
+  int out_mode;
+  double* log_scale_out;
+  int32_t* flags_out;
+};
+cudaError_t launch_generic(const ExecCtx& c, const Launch& l);
+cudaError_t launch_chain(const ExecCtx& c, const Launch& l, bool vec_ok);
+cudaError_t launch_interp(const ExecCtx& c, const Launch& l);
+cudaError_t launch_gemm(const ExecCtx& c, const Launch& l);
+cudaError_t launch_finalize(const ExecCtx& c, const Launch& l);
+cudaError_t launch_materialize(const ExecCtx& c, const Launch& l, bool vec_ok);
+bool gemm_supported(const Plan& p, const StepDev& s, const GemmDev& g);
+
+void set_cuda_error(cudaError_t e, const char* where);
+
+}  // namespace ctn

@@ -1,0 +1,681 @@
+// Device kernels of the B200 contraction engine (sm_100a).
+//
+//  generic_step   one (n-ary) einsum step with arbitrary element strides:
+//                 C[o] = alpha * sum_k prod_i A_i[off_i(o,k)], one output element
+//                 per thread, fused epilogue: alpha = prod of the inputs' pending
+//                 1/kappa, per-CTA sum|C|, last-arriving CTA turns the partials
+//                 into kappa = mean|C| and adds ln(kappa) to the log-scale
+//                 register (stabilize, contractn/einsum.py:89-107).
+//  chain          n-ary same-layout Hadamard product (copy-node hubs,
+//                 "ab,ab,...,ab->ab"): every operand is streamed from HBM exactly
+//                 once with 128-bit loads, products carry a per-element exponent
+//                 so no intermediate rescale pass is needed.
+//  interp         a run of tiny steps executed by ONE CTA in one launch (the
+//                 1000-step 3x3 chain): no launch or grid-wide sync per step.
+//  finalize       T / kappa (and * exp(c) for the dense output mode).
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+
+#include "ctn_internal.h"
+
+namespace ctn {
+
+struct DevState {
+  StateHdr* hdr;
+  double* inv_kappa;
+  double* kappa;
+  uint32_t* tickets;
+  double* partials;
+  int32_t* partial_exp;
+  void** ptrs;
+  char* arena;
+};
+
+static DevState dev_state(const ExecCtx& c) {
+  const StateLayout& st = c.plan->state;
+  DevState d;
+  d.hdr = (StateHdr*)(c.ws + st.hdr);
+  d.inv_kappa = (double*)(c.ws + st.inv_kappa);
+  d.kappa = (double*)(c.ws + st.kappa);
+  d.tickets = (uint32_t*)(c.ws + st.tickets);
+  d.partials = (double*)(c.ws + st.partials);
+  d.partial_exp = (int32_t*)(c.ws + st.partial_exp);
+  d.ptrs = (void**)(c.ws + st.ptrs);
+  d.arena = c.ws + st.total;
+  return d;
+}
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block in a fixed order (deterministic). Result valid in all threads.
+__device__ __forceinline__ double block_sum(double v, double* sm /* >= 33 doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) sm[32] = t;
+  }
+  __syncthreads();
+  return sm[32];
+}
+
+__device__ __forceinline__ int block_max_int(int v, int* sm /* >= 33 ints */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    int t = lane < (int)(blockDim.x >> 5) ? sm[lane] : INT_MIN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) sm[32] = t;
+  }
+  __syncthreads();
+  return sm[32];
+}
+
+// stabilize (contractn/einsum.py:89-107) for a tensor whose sum|T| is `norm`:
+// records kappa = norm/numel as the tensor's pending scale instead of dividing
+// (the consumer folds 1/kappa into its alpha) and moves ln(kappa) to the register.
+__device__ __forceinline__ void record_scale(const DevState& d, int slot, double norm, int64_t numel) {
+  const bool rescale = norm > kMinNorm;  // einsum.py:102 (NaN compares false, as in numpy)
+  const double kappa = norm / (double)numel;
+  d.kappa[slot] = rescale ? kappa : 1.0;
+  d.inv_kappa[slot] = rescale ? 1.0 / kappa : 1.0;
+  if (rescale) d.hdr->log_scale += log(kappa);
+}
+
+template <typename T, bool COHERENT>
+__device__ __forceinline__ double load_elem(const T* p) {
+  if (COHERENT) return (double)__ldcg(p);  // produced earlier in this same launch
+  return (double)__ldg(p);
+}
+
+// One output element of a generic step.
+template <typename T, bool COHERENT, typename IDX>
+__device__ __forceinline__ double step_element(const StepDev& s, const ModeDev* __restrict__ modes,
+                                               const T* const* in, IDX o) {
+  const int n_in = s.n_in;
+  int64_t off[kMaxIn];
+#pragma unroll
+  for (int i = 0; i < kMaxIn; ++i) off[i] = 0;
+  IDX rem = o;
+  for (int m = s.n_out_modes - 1; m >= 0; --m) {
+    const ModeDev& md = modes[m];
+    const IDX e = (IDX)md.extent;
+    const IDX idx = rem % e;
+    rem /= e;
+#pragma unroll
+    for (int i = 0; i < kMaxIn; ++i)
+      if (i < n_in) off[i] += (int64_t)idx * md.stride[i];
+  }
+  if (s.n_k_modes == 0) {
+    double pr = 1.0;
+#pragma unroll
+    for (int i = 0; i < kMaxIn; ++i)
+      if (i < n_in) pr *= load_elem<T, COHERENT>(in[i] + off[i]);
+    return pr;
+  }
+  if (s.k_numel == 0) return 0.0;  // a summed index of extent 0: empty sum
+  const ModeDev* km = modes + s.n_out_modes;
+  const ModeDev& inner = km[s.n_k_modes - 1];
+  const IDX inner_n = (IDX)inner.extent;
+  const IDX outer_n = (IDX)(s.k_numel / inner.extent);
+  double acc = 0.0;
+  for (IDX ko = 0; ko < outer_n; ++ko) {
+    int64_t o2[kMaxIn];
+#pragma unroll
+    for (int i = 0; i < kMaxIn; ++i) o2[i] = off[i];
+    IDX r = ko;
+    for (int m = s.n_k_modes - 2; m >= 0; --m) {
+      const ModeDev& md = km[m];
+      const IDX e = (IDX)md.extent;
+      const IDX idx = r % e;
+      r /= e;
+#pragma unroll
+      for (int i = 0; i < kMaxIn; ++i)
+        if (i < n_in) o2[i] += (int64_t)idx * md.stride[i];
+    }
+    for (IDX kk = 0; kk < inner_n; ++kk) {
+      double pr = 1.0;
+#pragma unroll
+      for (int i = 0; i < kMaxIn; ++i)
+        if (i < n_in) pr *= load_elem<T, COHERENT>(in[i] + o2[i] + (int64_t)kk * inner.stride[i]);
+      acc += pr;
+    }
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------
+// generic step kernel
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) generic_step_kernel(const StepDev* __restrict__ steps,
+                                                                const ModeDev* __restrict__ all_modes, int step_idx,
+                                                                DevState d) {
+  __shared__ double red[33];
+  __shared__ bool last_block;
+  const StepDev& s = steps[step_idx];
+  const ModeDev* modes = all_modes + s.mode_off;
+  const T* in[kMaxIn];
+  double alpha = 1.0;
+#pragma unroll
+  for (int i = 0; i < kMaxIn; ++i) {
+    in[i] = nullptr;
+    if (i < s.n_in) {
+      in[i] = (const T*)d.ptrs[s.in_slot[i]];
+      alpha *= d.inv_kappa[s.in_slot[i]];
+    }
+  }
+  T* out = (T*)d.ptrs[s.out_slot];
+  const int64_t numel = s.out_numel;
+  double local = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool small = numel < (int64_t)0x7fffffff && s.k_numel < (int64_t)0x7fffffff;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < numel; o += stride) {
+    double v = small ? step_element<T, false, uint32_t>(s, modes, in, (uint32_t)o)
+                     : step_element<T, false, uint64_t>(s, modes, in, (uint64_t)o);
+    const T r = (T)(v * alpha);
+    out[o] = r;
+    local += fabs((double)r);
+  }
+  const double bsum = block_sum(local, red);
+  if (threadIdx.x == 0) {
+    d.partials[blockIdx.x] = bsum;
+    __threadfence();
+    const uint32_t t = atomicAdd(&d.tickets[s.ticket], 1u);
+    last_block = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_block) {
+    __threadfence();
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(&d.partials[i]);
+    const double norm = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      record_scale(d, s.out_slot, norm, numel);
+      d.tickets[s.ticket] = 0;
+    }
+  }
+}
+
+cudaError_t launch_generic(const ExecCtx& c, const Launch& l) {
+  const Plan& p = *c.plan;
+  const StepDev& s = p.steps[l.first_step];
+  int64_t blocks = (s.out_numel + kThreads - 1) / kThreads;
+  int64_t cap = std::min<int64_t>((int64_t)p.sm_count * 8, kMaxPartials);
+  int grid = (int)std::max<int64_t>(1, std::min(blocks, cap));
+  DevState d = dev_state(c);
+  if (p.dtype == CTN_F32)
+    generic_step_kernel<float><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d);
+  else
+    generic_step_kernel<double><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// finalize: canonical split output (and destabilize for the dense mode)
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T finish_value(T raw, double kappa, bool dense, double expc) {
+  T v = raw / (T)kappa;                      // einsum.py:103  tensor / rescale
+  if (dense) v = (T)((double)v * expc);      // einsum.py:114  tensor * exp(log_scale)
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) finalize_kernel(DevState d, int slot, int64_t numel, int dense,
+                                                            double* log_scale_out, int32_t* flags_out) {
+  T* out = (T*)d.ptrs[slot];
+  const double kappa = d.kappa[slot];
+  const double c = d.hdr->log_scale;
+  const double expc = dense ? exp(c) : 1.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    out[i] = finish_value<T>(out[i], kappa, dense != 0, expc);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *log_scale_out = c;
+    if (flags_out) *flags_out = d.hdr->flags;
+  }
+}
+
+cudaError_t launch_finalize(const ExecCtx& c, const Launch& l) {
+  const Plan& p = *c.plan;
+  const StepDev& s = p.steps[l.first_step];
+  int64_t blocks = (s.out_numel + kThreads - 1) / kThreads;
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)p.sm_count * 8));
+  DevState d = dev_state(c);
+  if (p.dtype == CTN_F32)
+    finalize_kernel<float><<<grid, kThreads, 0, c.stream>>>(d, s.out_slot, s.out_numel, c.out_mode == CTN_OUT_DENSE,
+                                                           c.log_scale_out, c.flags_out);
+  else
+    finalize_kernel<double><<<grid, kThreads, 0, c.stream>>>(d, s.out_slot, s.out_numel, c.out_mode == CTN_OUT_DENSE,
+                                                            c.log_scale_out, c.flags_out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// interpreter: a run of tiny steps in one CTA
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) interp_kernel(const StepDev* __restrict__ steps,
+                                                          const ModeDev* __restrict__ all_modes, int first, int last,
+                                                          DevState d, int dense, double* log_scale_out,
+                                                          int32_t* flags_out) {
+  __shared__ double red[33];
+  for (int si = first; si <= last; ++si) {
+    const StepDev& s = steps[si];
+    const ModeDev* modes = all_modes + s.mode_off;
+    const T* in[kMaxIn];
+    double alpha = 1.0;
+#pragma unroll
+    for (int i = 0; i < kMaxIn; ++i) {
+      in[i] = nullptr;
+      if (i < s.n_in) {
+        in[i] = (const T*)d.ptrs[s.in_slot[i]];
+        alpha *= __ldcg(&d.inv_kappa[s.in_slot[i]]);
+      }
+    }
+    T* out = (T*)d.ptrs[s.out_slot];
+    const int numel = (int)s.out_numel;
+    double local = 0.0;
+    for (int o = threadIdx.x; o < numel; o += blockDim.x) {
+      const double v = step_element<T, true, uint32_t>(s, modes, in, (uint32_t)o);
+      const T r = (T)(v * alpha);
+      out[o] = r;
+      local += fabs((double)r);
+    }
+    const double norm = block_sum(local, red);
+    if (threadIdx.x == 0) record_scale(d, s.out_slot, norm, s.out_numel);
+    __threadfence_block();
+    __syncthreads();
+  }
+  const StepDev& s = steps[last];
+  if (s.is_final) {
+    T* out = (T*)d.ptrs[s.out_slot];
+    const double kappa = __ldcg(&d.kappa[s.out_slot]);
+    const double c = __ldcg(&d.hdr->log_scale);
+    const double expc = dense ? exp(c) : 1.0;
+    for (int i = threadIdx.x; i < (int)s.out_numel; i += blockDim.x)
+      out[i] = finish_value<T>(__ldcg(&out[i]), kappa, dense != 0, expc);
+    if (threadIdx.x == 0) {
+      *log_scale_out = c;
+      if (flags_out) *flags_out = d.hdr->flags;
+    }
+  }
+}
+
+cudaError_t launch_interp(const ExecCtx& c, const Launch& l) {
+  const Plan& p = *c.plan;
+  DevState d = dev_state(c);
+  if (p.dtype == CTN_F32)
+    interp_kernel<float><<<1, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
+                                                      c.out_mode == CTN_OUT_DENSE, c.log_scale_out, c.flags_out);
+  else
+    interp_kernel<double><<<1, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
+                                                       c.out_mode == CTN_OUT_DENSE, c.log_scale_out, c.flags_out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Hadamard chain
+// ---------------------------------------------------------------------------
+template <typename T, bool VEC>
+struct ChainCfg {
+  static constexpr int kEpv = VEC ? 16 / (int)sizeof(T) : 1;  // elements per vector
+  static constexpr int kVpt = VEC ? 2 : 4;                    // vectors per thread
+  static constexpr int kEpt = kEpv * kVpt;
+  static constexpr int kTile = kEpt * kThreads;
+};
+
+template <typename T, int EPV>
+struct Vec;
+template <>
+struct Vec<double, 2> { using type = double2; };
+template <>
+struct Vec<float, 4> { using type = float4; };
+template <>
+struct Vec<double, 1> { using type = double; };
+template <>
+struct Vec<float, 1> { using type = float; };
+
+template <typename T, int EPV>
+__device__ __forceinline__ void load_vec(const T* p, double (&dst)[EPV]) {
+  if constexpr (EPV == 1) {
+    dst[0] = (double)__ldcs(p);
+  } else if constexpr (sizeof(T) == 8) {
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    dst[0] = v.x; dst[1] = v.y;
+  } else {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+}
+
+template <typename T, int EPV>
+__device__ __forceinline__ void store_vec(T* p, const double (&src)[EPV]) {
+  if constexpr (EPV == 1) {
+    *p = (T)src[0];
+  } else if constexpr (sizeof(T) == 8) {
+    *reinterpret_cast<double2*>(p) = make_double2(src[0], src[1]);
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4((float)src[0], (float)src[1], (float)src[2], (float)src[3]);
+  }
+}
+
+// Pull the binary exponent of a normal double into an integer side-car.
+__device__ __forceinline__ void split_exponent(double& p, int& x) {
+  long long b = __double_as_longlong(p);
+  const int ef = (int)((b >> 52) & 0x7ff);
+  if (ef != 0 && ef != 0x7ff) {
+    x += ef - 1023;
+    b = (b & ~(0x7ffLL << 52)) | (1023LL << 52);
+    p = __longlong_as_double(b);
+  }
+}
+
+// merge (S, E) pairs meaning S * 2^E, keeping the larger exponent
+__device__ __forceinline__ void merge_scaled(double& S, int& E, double s, int e) {
+  if (s == 0.0) return;
+  if (S == 0.0) { S = s; E = e; return; }
+  if (e > E) { S = scalbn(S, E - e) + s; E = e; }
+  else S += scalbn(s, e - E);
+}
+
+constexpr int kChainUnroll = 4;
+constexpr int kRenormEvery = 4;
+
+template <typename T, bool VEC, bool TRACKED>
+__global__ void __launch_bounds__(kThreads) chain_kernel(const StepDev* __restrict__ steps,
+                                                         const int32_t* __restrict__ slot_list, int step_idx,
+                                                         DevState d) {
+  using Cfg = ChainCfg<T, VEC>;
+  constexpr int EPV = Cfg::kEpv, VPT = Cfg::kVpt, EPT = Cfg::kEpt;
+  __shared__ const T* in_ptr[kChainMaxIn];
+  __shared__ double red[33];
+  __shared__ int redi[33];
+  __shared__ bool last_block;
+  const StepDev& s = steps[step_idx];
+  const int n_in = s.n_in;
+  const int64_t numel = s.out_numel;
+  T* out = (T*)d.ptrs[s.out_slot];
+
+  // stage the operand pointers and the combined pending scale of the inputs
+  double a_part = 1.0;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
+    const int slot = slot_list[s.slot_off + i];
+    in_ptr[i] = (const T*)d.ptrs[slot];
+    a_part *= d.inv_kappa[slot];
+  }
+  // product over the block (fixed order)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a_part *= __shfl_xor_sync(0xffffffffu, a_part, o);
+    if (lane == 0) red[warp] = a_part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 1.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a *= red[w];
+      red[32] = a;
+    }
+    __syncthreads();
+  }
+  const double alpha = red[32];
+  __syncthreads();
+
+  int32_t* tile_exp = TRACKED ? (int32_t*)(d.arena + s.scratch_off) : nullptr;
+  const int64_t n_tiles = (numel + Cfg::kTile - 1) / Cfg::kTile;
+  double blk_S = 0.0, blk_Sp = 0.0;  // running sums of this CTA (thread 0 only)
+  int blk_E = 0, blk_Ep = 0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * Cfg::kTile;
+    double p[VPT][EPV];
+    int x[VPT][EPV];
+    double pp[VPT][EPV];  // product before the last operand (TRACKED)
+    int xp[VPT][EPV];
+    bool live[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int64_t e0 = base + ((int64_t)v * kThreads + threadIdx.x) * EPV;
+      live[v] = e0 < numel;  // numel % EPV == 0 is guaranteed by the launcher
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) { p[v][e] = alpha; x[v][e] = 0; pp[v][e] = 0.0; xp[v][e] = 0; }
+    }
+    for (int i0 = 0; i0 < n_in; i0 += kChainUnroll) {
+      double val[kChainUnroll][VPT][EPV];
+#pragma unroll
+      for (int u = 0; u < kChainUnroll; ++u) {
+        const int i = i0 + u;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          const int64_t e0 = base + ((int64_t)v * kThreads + threadIdx.x) * EPV;
+          if (i < n_in && live[v]) load_vec<T, EPV>(in_ptr[i] + e0, val[u][v]);
+          else {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) val[u][v][e] = 1.0;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kChainUnroll; ++u) {
+        const int i = i0 + u;
+        if (i < n_in) {
+          if (TRACKED && i == n_in - 1) {
+#pragma unroll
+            for (int v = 0; v < VPT; ++v)
+#pragma unroll
+              for (int e = 0; e < EPV; ++e) { pp[v][e] = p[v][e]; xp[v][e] = x[v][e]; }
+          }
+#pragma unroll
+          for (int v = 0; v < VPT; ++v)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) p[v][e] *= val[u][v][e];
+        }
+      }
+      if (TRACKED) {
+        // kChainUnroll == kRenormEvery: pull exponents out after every group
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) split_exponent(p[v][e], x[v][e]);
+      }
+    }
+    if (!TRACKED) {
+      double local = 0.0;
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        if (!live[v]) continue;
+        const int64_t e0 = base + ((int64_t)v * kThreads + threadIdx.x) * EPV;
+        double r[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) { r[e] = (double)(T)p[v][e]; local += fabs(r[e]); }
+        store_vec<T, EPV>(out + e0, r);
+      }
+      const double tsum = block_sum(local, red);
+      if (threadIdx.x == 0) blk_S += tsum;
+    } else {
+      // tile exponent = max exponent of its non-zero finite entries
+      int ex = INT_MIN, exp_ = INT_MIN;
+#pragma unroll
+      for (int v = 0; v < VPT; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          split_exponent(pp[v][e], xp[v][e]);
+          if (live[v] && p[v][e] != 0.0 && isfinite(p[v][e])) ex = max(ex, x[v][e]);
+          if (live[v] && pp[v][e] != 0.0 && isfinite(pp[v][e])) exp_ = max(exp_, xp[v][e]);
+        }
+      int tE = block_max_int(ex, redi);
+      int tEp = block_max_int(exp_, redi);
+      if (tE == INT_MIN) tE = 0;
+      if (tEp == INT_MIN) tEp = 0;
+      double local = 0.0, localp = 0.0;
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        if (!live[v]) continue;
+        const int64_t e0 = base + ((int64_t)v * kThreads + threadIdx.x) * EPV;
+        double r[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          r[e] = (double)(T)scalbn(p[v][e], max(x[v][e] - tE, -4000));
+          local += fabs(r[e]);
+          localp += fabs(scalbn(pp[v][e], max(xp[v][e] - tEp, -4000)));
+        }
+        store_vec<T, EPV>(out + e0, r);
+      }
+      const double tsum = block_sum(local, red);
+      const double tsump = block_sum(localp, red);
+      if (threadIdx.x == 0) {
+        tile_exp[tile] = tE;
+        merge_scaled(blk_S, blk_E, tsum, tE);
+        merge_scaled(blk_Sp, blk_Ep, tsump, tEp);
+      }
+    }
+  }
+
+  // publish the CTA partials; the last CTA to arrive reduces them in index order
+  if (threadIdx.x == 0) {
+    d.partials[blockIdx.x] = blk_S;
+    if (TRACKED) {
+      d.partials[kMaxPartials + blockIdx.x] = blk_Sp;
+      d.partial_exp[blockIdx.x] = blk_E;
+      d.partial_exp[kMaxPartials + blockIdx.x] = blk_Ep;
+    }
+    __threadfence();
+    const uint32_t t = atomicAdd(&d.tickets[s.ticket], 1u);
+    last_block = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  if (!TRACKED) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(&d.partials[i]);
+    const double norm = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      record_scale(d, s.out_slot, norm, numel);
+      d.tickets[s.ticket] = 0;
+    }
+  } else if (threadIdx.x == 0) {
+    // few thousand partials at most: serial, fixed order
+    double S = 0.0, Sp = 0.0;
+    int E = 0, Ep = 0;
+    for (int i = 0; i < (int)gridDim.x; ++i) {
+      merge_scaled(S, E, __ldcg(&d.partials[i]), __ldcg(&d.partial_exp[i]));
+      merge_scaled(Sp, Ep, __ldcg(&d.partials[kMaxPartials + i]), __ldcg(&d.partial_exp[kMaxPartials + i]));
+    }
+    // reference decision for the LAST fused step (einsum.py:102): its input was
+    // the normalised running product, so its norm is  sum|T_n| / mean|T_{n-1}|
+    const double log_ratio =
+        (log(S) + E * M_LN2) - (log(Sp) + Ep * M_LN2) + log((double)numel);
+    const bool fine = isfinite(S) && isfinite(Sp) && S > 0.0 && Sp > 0.0 && log_ratio > log(kMinNorm) + 1e-6;
+    const double mean = S / (double)numel;
+    d.hdr->chain_exp = E;
+    d.hdr->chain_mean = fine ? mean : 1.0;
+    if (fine) d.hdr->log_scale += E * M_LN2 + log(mean);
+    else d.hdr->flags |= CTN_RESULT_DEGENERATE;
+    d.kappa[s.out_slot] = 1.0;      // the materialise pass leaves a normalised tensor
+    d.inv_kappa[s.out_slot] = 1.0;
+    d.tickets[s.ticket] = 0;
+  }
+}
+
+// Second pass of a tracked chain: bring every tile to the common exponent and
+// divide by the mean (this IS the stabilize of the fused run); for the plan's
+// final tensor also apply the output mode.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads) chain_materialize_kernel(const StepDev* __restrict__ steps, int step_idx,
+                                                                     DevState d, int dense, double* log_scale_out,
+                                                                     int32_t* flags_out) {
+  using Cfg = ChainCfg<T, VEC>;
+  const StepDev& s = steps[step_idx];
+  T* out = (T*)d.ptrs[s.out_slot];
+  const int32_t* tile_exp = (const int32_t*)(d.arena + s.scratch_off);
+  const int E = d.hdr->chain_exp;
+  const double mean = d.hdr->chain_mean;
+  const double c = d.hdr->log_scale;
+  const bool final_dense = s.is_final && dense;
+  const double expc = final_dense ? exp(c) : 1.0;
+  const int64_t numel = s.out_numel;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) {
+    const int64_t tile = i / Cfg::kTile;
+    const double v = scalbn((double)out[i], max(tile_exp[tile] - E, -4000));
+    T r = (T)v / (T)mean;
+    if (final_dense) r = (T)((double)r * expc);
+    out[i] = r;
+  }
+  if (s.is_final && blockIdx.x == 0 && threadIdx.x == 0) {
+    *log_scale_out = c;
+    if (flags_out) *flags_out = d.hdr->flags;
+  }
+}
+
+template <typename T, bool VEC>
+static cudaError_t launch_chain_t(const ExecCtx& c, const Launch& l) {
+  using Cfg = ChainCfg<T, VEC>;
+  const Plan& p = *c.plan;
+  const StepDev& s = p.steps[l.first_step];
+  const int64_t n_tiles = (s.out_numel + Cfg::kTile - 1) / Cfg::kTile;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, kMaxPartials));
+  DevState d = dev_state(c);
+  if (s.tracked)
+    chain_kernel<T, VEC, true><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_slot_list, l.first_step, d);
+  else
+    chain_kernel<T, VEC, false><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_slot_list, l.first_step, d);
+  return cudaGetLastError();
+}
+
+template <typename T, bool VEC>
+static cudaError_t launch_materialize_t(const ExecCtx& c, const Launch& l) {
+  const Plan& p = *c.plan;
+  const StepDev& s = p.steps[l.first_step];
+  DevState d = dev_state(c);
+  const int64_t blocks = (s.out_numel + kThreads - 1) / kThreads;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)p.sm_count * 8));
+  chain_materialize_kernel<T, VEC><<<grid, kThreads, 0, c.stream>>>(p.d_steps, l.first_step, d,
+                                                                   c.out_mode == CTN_OUT_DENSE, c.log_scale_out,
+                                                                   c.flags_out);
+  return cudaGetLastError();
+}
+
+static bool chain_vec(const Plan& p, const StepDev& s, bool vec_ok) {
+  const int epv = p.dtype == CTN_F32 ? 4 : 2;
+  return vec_ok && (s.out_numel % epv == 0);
+}
+
+cudaError_t launch_chain(const ExecCtx& c, const Launch& l, bool vec_ok) {
+  const Plan& p = *c.plan;
+  const bool vec = chain_vec(p, p.steps[l.first_step], vec_ok);
+  if (p.dtype == CTN_F32) return vec ? launch_chain_t<float, true>(c, l) : launch_chain_t<float, false>(c, l);
+  return vec ? launch_chain_t<double, true>(c, l) : launch_chain_t<double, false>(c, l);
+}
+
+// must pick the same tile geometry as the chain launch it follows
+cudaError_t launch_materialize(const ExecCtx& c, const Launch& l, bool vec_ok) {
+  const Plan& p = *c.plan;
+  const bool vec = chain_vec(p, p.steps[l.first_step], vec_ok);
+  if (p.dtype == CTN_F32) return vec ? launch_materialize_t<float, true>(c, l) : launch_materialize_t<float, false>(c, l);
+  return vec ? launch_materialize_t<double, true>(c, l) : launch_materialize_t<double, false>(c, l);
+}
+
+}  // namespace ctn

@@ -1,0 +1,732 @@
+// Plan compiler and C ABI of the B200 contraction engine.
+//
+// Turns a contraction list (contractn/einsum.py:341-344: positions to pop,
+// per-step einsum string) into a device-resident plan: per-step loop modes with
+// element strides (no transposes are ever materialised), kernel class per step,
+// lifetime-based placement of intermediates in one workspace arena, fusion of
+// same-layout Hadamard runs (copy-node hubs) into n-ary launches and of runs of
+// tiny steps into a single-CTA interpreter launch.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <set>
+
+#include "ctn_internal.h"
+
+namespace ctn {
+
+static thread_local std::string g_cuda_error;
+
+void set_cuda_error(cudaError_t e, const char* where) {
+  g_cuda_error = std::string(where) + ": " + cudaGetErrorString(e);
+}
+
+#define CTN_CUDA(expr)                      \
+  do {                                      \
+    cudaError_t _e = (expr);                \
+    if (_e != cudaSuccess) {                \
+      set_cuda_error(_e, #expr);            \
+      return CTN_ERR_CUDA;                  \
+    }                                       \
+  } while (0)
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// arena: first-fit free list with coalescing (intermediates have nested or
+// overlapping lifetimes; stream order makes reuse safe)
+// ---------------------------------------------------------------------------
+struct Arena {
+  std::map<size_t, size_t> free_;  // offset -> size
+  size_t top = 0;
+  size_t alloc(size_t bytes) {
+    bytes = align_up(std::max<size_t>(bytes, 1), 256);
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second >= bytes) {
+        size_t off = it->first, rest = it->second - bytes;
+        free_.erase(it);
+        if (rest) free_[off + bytes] = rest;
+        return off;
+      }
+    }
+    // grow: extend a free block that touches the top if there is one
+    auto last = free_.empty() ? free_.end() : std::prev(free_.end());
+    if (last != free_.end() && last->first + last->second == top) {
+      size_t off = last->first;
+      free_.erase(last);
+      top = off + bytes;
+      return off;
+    }
+    size_t off = top;
+    top += bytes;
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = align_up(std::max<size_t>(bytes, 1), 256);
+    auto it = free_.emplace(off, bytes).first;
+    auto nx = std::next(it);
+    if (nx != free_.end() && it->first + it->second == nx->first) {
+      it->second += nx->second;
+      free_.erase(nx);
+    }
+    if (it != free_.begin()) {
+      auto pv = std::prev(it);
+      if (pv->first + pv->second == it->first) {
+        pv->second += it->second;
+        free_.erase(it);
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// step lowering
+// ---------------------------------------------------------------------------
+struct LoweredStep {
+  std::vector<int32_t> in_slots;
+  int32_t out_slot;
+  std::vector<ModeDev> out_modes, k_modes;  // fused, extent-1 dropped
+  int64_t out_numel = 1, k_numel = 1;
+  double flops = 0;
+  bool elementwise = false;  // no summed mode, every input laid out like the output
+  bool tiny = false;
+  GemmDev gemm;
+  bool has_gemm = false;
+};
+
+static void fuse_modes(std::vector<ModeDev>& modes, int n_in, bool out_modes) {
+  // drop extent-1 modes, then merge neighbours (outer, inner) whenever
+  // stride_outer == stride_inner * extent_inner in every input
+  std::vector<ModeDev> kept;
+  for (auto& m : modes)
+    if (m.extent != 1) kept.push_back(m);
+  if (!out_modes) {
+    // summed modes may be visited in any order: sort by stride in the first
+    // input that has a non-zero stride so that contiguous runs become adjacent
+    std::stable_sort(kept.begin(), kept.end(), [n_in](const ModeDev& a, const ModeDev& b) {
+      for (int i = 0; i < n_in; ++i)
+        if (a.stride[i] != b.stride[i]) return a.stride[i] > b.stride[i];
+      return false;
+    });
+  }
+  std::vector<ModeDev> fused;
+  for (auto& m : kept) {
+    if (!fused.empty()) {
+      ModeDev& o = fused.back();
+      bool ok = true;
+      for (int i = 0; i < n_in; ++i) ok = ok && (o.stride[i] == m.stride[i] * m.extent);
+      if (ok) {
+        o.extent *= m.extent;
+        for (int i = 0; i < n_in; ++i) o.stride[i] = m.stride[i];
+        continue;
+      }
+    }
+    fused.push_back(m);
+  }
+  modes.swap(fused);
+}
+
+static void fuse_gemm_group(GemmMode* g, int32_t& n, bool keep_order) {
+  std::vector<GemmMode> kept;
+  for (int i = 0; i < n; ++i)
+    if (g[i].extent != 1) kept.push_back(g[i]);
+  if (!keep_order) {
+    std::stable_sort(kept.begin(), kept.end(), [](const GemmMode& a, const GemmMode& b) {
+      if (a.sa != b.sa) return a.sa > b.sa;
+      return a.sb > b.sb;
+    });
+  }
+  std::vector<GemmMode> fused;
+  for (auto& m : kept) {
+    if (!fused.empty()) {
+      GemmMode& o = fused.back();
+      if (o.sa == m.sa * m.extent && o.sb == m.sb * m.extent && o.sc == m.sc * m.extent) {
+        o.extent *= m.extent;
+        o.sa = m.sa; o.sb = m.sb; o.sc = m.sc;
+        continue;
+      }
+    }
+    fused.push_back(m);
+  }
+  n = (int32_t)fused.size();
+  for (int i = 0; i < n; ++i) g[i] = fused[i];
+}
+
+static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& live, LoweredStep& ls) {
+  if (sd.n_inputs < 1 || !sd.positions || !sd.input_ranks) return CTN_ERR_INVALID;
+  // pop operands exactly like `[operands.pop(x) for x in inds]` (einsum.py:344)
+  for (int i = 0; i < sd.n_inputs; ++i) {
+    int32_t pos = sd.positions[i];
+    if (pos < 0 || pos >= (int32_t)live.size()) return CTN_ERR_INVALID;
+    ls.in_slots.push_back(live[pos]);
+    live.erase(live.begin() + pos);
+  }
+  const int n_in = sd.n_inputs;
+  // label -> extent (broadcast-aware), per-input stride sums
+  std::map<int32_t, int64_t> extent;
+  std::vector<std::map<int32_t, int64_t>> in_stride(n_in);
+  std::vector<std::map<int32_t, int64_t>> in_extent(n_in);
+  std::vector<std::vector<int32_t>> in_labels(n_in);
+  const int32_t* lab = sd.input_labels;
+  for (int i = 0; i < n_in; ++i) {
+    const Slot& s = p.slots[ls.in_slots[i]];
+    if (sd.input_ranks[i] != (int32_t)s.extents.size()) return CTN_ERR_INVALID;
+    for (int a = 0; a < sd.input_ranks[i]; ++a, ++lab) {
+      int32_t l = *lab;
+      in_labels[i].push_back(l);
+      if (l < 0) return CTN_ERR_INVALID;
+      int64_t e = s.extents[a];
+      auto it = extent.find(l);
+      if (it == extent.end()) extent[l] = e;
+      else if (it->second == 1) it->second = e;
+      else if (e != 1 && e != it->second) return CTN_ERR_SHAPE;
+      // a repeated label inside one operand walks its diagonal: strides add up
+      if (in_extent[i].count(l) && in_extent[i][l] != e) return CTN_ERR_SHAPE;
+      in_extent[i][l] = e;
+      in_stride[i][l] += s.strides[a];
+    }
+  }
+  // output slot
+  Slot out;
+  std::set<int32_t> out_set;
+  for (int a = 0; a < sd.out_rank; ++a) {
+    int32_t l = sd.out_labels[a];
+    if (!extent.count(l) || out_set.count(l)) return CTN_ERR_INVALID;
+    out_set.insert(l);
+    out.labels.push_back(l);
+    out.extents.push_back(extent[l]);
+  }
+  out.strides.assign(sd.out_rank, 1);
+  for (int a = sd.out_rank - 2; a >= 0; --a) out.strides[a] = out.strides[a + 1] * out.extents[a + 1];
+  for (auto e : out.extents) out.numel *= e;
+  ls.out_slot = (int32_t)p.slots.size();
+  p.slots.push_back(out);
+  live.push_back(ls.out_slot);
+
+  auto make_mode = [&](int32_t l) {
+    ModeDev m{};
+    m.extent = extent[l];
+    for (int i = 0; i < n_in && i < kMaxIn; ++i) {
+      auto it = in_stride[i].find(l);
+      // absent, or broadcast (extent 1 against a larger one): stride 0
+      m.stride[i] = (it == in_stride[i].end() || in_extent[i][l] != m.extent) ? 0 : it->second;
+    }
+    return m;
+  };
+  bool any_sum = false;
+  double all = 1;
+  for (auto& kv : extent) {
+    all *= (double)kv.second;
+    if (!out_set.count(kv.first)) any_sum = true;
+  }
+  ls.flops = all * (std::max(1, n_in - 1) + (any_sum ? 1 : 0));
+  ls.out_numel = out.numel;
+
+  if (n_in <= kMaxIn) {
+    for (int a = 0; a < sd.out_rank; ++a) ls.out_modes.push_back(make_mode(sd.out_labels[a]));
+    for (auto& kv : extent)
+      if (!out_set.count(kv.first)) ls.k_modes.push_back(make_mode(kv.first));
+    for (auto& m : ls.k_modes) ls.k_numel *= m.extent;
+    fuse_modes(ls.out_modes, n_in, true);
+    fuse_modes(ls.k_modes, n_in, false);
+  }
+  // same-layout Hadamard product?  every label in the output, every input
+  // carrying all output labels in output order with identical (contiguous) strides
+  ls.elementwise = !any_sum;
+  if (ls.elementwise) {
+    for (int i = 0; i < n_in && ls.elementwise; ++i) {
+      const Slot& s = p.slots[ls.in_slots[i]];
+      if (in_labels[i] != out.labels || s.extents != out.extents || s.strides != out.strides)
+        ls.elementwise = false;
+    }
+  }
+  if (!ls.elementwise && n_in > kMaxIn) return CTN_ERR_UNSUPPORTED;
+  double work = (double)ls.out_numel * (double)ls.k_numel * n_in;
+  ls.tiny = n_in <= kMaxIn && work <= 8192.0 && ls.out_numel <= 2048;
+
+  // GEMM view for pairwise steps with a summed index and no index that is
+  // summed out of a single operand only
+  if (n_in == 2 && any_sum) {
+    GemmDev g{};
+    bool ok = true;
+    auto push = [&](GemmMode* grp, int32_t& n, GemmMode m) {
+      if (n >= kGemmMaxModes) { ok = false; return; }
+      grp[n++] = m;
+    };
+    int64_t sc = 1;
+    std::map<int32_t, int64_t> c_stride;
+    for (int a = sd.out_rank - 1; a >= 0; --a) { c_stride[sd.out_labels[a]] = sc; sc *= out.extents[a]; }
+    auto stride_of = [&](int i, int32_t l) -> int64_t {
+      auto it = in_stride[i].find(l);
+      return (it == in_stride[i].end() || in_extent[i][l] != extent[l]) ? 0 : it->second;
+    };
+    // groups in output order for M, N, batch; K order is free
+    for (int a = 0; a < sd.out_rank; ++a) {
+      int32_t l = sd.out_labels[a];
+      bool inA = in_stride[0].count(l) > 0, inB = in_stride[1].count(l) > 0;
+      GemmMode m{extent[l], stride_of(0, l), stride_of(1, l), c_stride[l]};
+      if (inA && inB) push(g.batch, g.n_batch, m);
+      else if (inA) push(g.m, g.n_m, m);
+      else push(g.n, g.n_n, m);
+    }
+    for (auto& kv : extent) {
+      if (out_set.count(kv.first)) continue;
+      int32_t l = kv.first;
+      GemmMode m{kv.second, stride_of(0, l), stride_of(1, l), 0};
+      push(g.k, g.n_k, m);
+    }
+    if (ok) {
+      fuse_gemm_group(g.batch, g.n_batch, true);
+      fuse_gemm_group(g.m, g.n_m, true);
+      fuse_gemm_group(g.n, g.n_n, true);
+      fuse_gemm_group(g.k, g.n_k, false);
+      g.B = g.M = g.N = g.K = 1;
+      for (int i = 0; i < g.n_batch; ++i) g.B *= g.batch[i].extent;
+      for (int i = 0; i < g.n_m; ++i) g.M *= g.m[i].extent;
+      for (int i = 0; i < g.n_n; ++i) g.N *= g.n[i].extent;
+      for (int i = 0; i < g.n_k; ++i) g.K *= g.k[i].extent;
+      ls.gemm = g;
+      ls.has_gemm = true;
+    }
+  }
+  return CTN_OK;
+}
+
+static void layout_state(Plan& p) {
+  StateLayout& s = p.state;
+  size_t n = p.slots.size();
+  size_t off = 0;
+  s.hdr = off; off += align_up(sizeof(StateHdr), 16);
+  s.inv_kappa = off; off += n * sizeof(double);
+  s.kappa = off; off += n * sizeof(double);
+  s.ptrs = off; off += n * sizeof(void*);
+  s.tickets = off; off += align_up((size_t)std::max(1, p.n_tickets) * sizeof(uint32_t), 16);
+  s.init_bytes = off;
+  s.partials = off; off += 4 * (size_t)kMaxPartials * sizeof(double);
+  s.partial_exp = off; off += 2 * (size_t)kMaxPartials * sizeof(int32_t);
+  s.total = align_up(off, 256);
+}
+
+static int build_plan(const ctn_plan_desc& d, Plan& p) {
+  if (d.abi_version != CTN_ABI_VERSION) return CTN_ERR_INVALID;
+  if (d.dtype != CTN_F32 && d.dtype != CTN_F64) return CTN_ERR_UNSUPPORTED;
+  if (d.n_operands < 1 || d.n_steps < 1 || !d.operand_ranks || !d.steps) return CTN_ERR_INVALID;
+  p.dtype = d.dtype;
+  p.elem = d.dtype == CTN_F32 ? 4 : 8;
+  p.flags = d.flags;
+  p.n_operands = d.n_operands;
+  const int64_t* ext = d.operand_extents;
+  const int64_t* str = d.operand_strides;
+  std::vector<int32_t> live;
+  for (int i = 0; i < d.n_operands; ++i) {
+    Slot s;
+    int r = d.operand_ranks[i];
+    if (r < 0 || (r > 0 && !ext)) return CTN_ERR_INVALID;
+    s.extents.assign(ext, ext + r);
+    ext += r;
+    for (auto e : s.extents) {
+      if (e < 0) return CTN_ERR_INVALID;
+      s.numel *= e;
+    }
+    if (str) {
+      s.strides.assign(str, str + r);
+      str += r;
+      for (auto v : s.strides)
+        if (v < 0) return CTN_ERR_UNSUPPORTED;
+    } else {
+      s.strides.assign(r, 1);
+      for (int a = r - 2; a >= 0; --a) s.strides[a] = s.strides[a + 1] * s.extents[a + 1];
+    }
+    s.operand = i;
+    live.push_back(i);
+    p.slots.push_back(s);
+  }
+
+  // lower every step, fusing Hadamard runs on the way
+  std::vector<LoweredStep> lowered;
+  const bool fuse = !(d.flags & CTN_PLAN_EXACT_STEPS);
+  for (int t = 0; t < d.n_steps; ++t) {
+    LoweredStep ls;
+    int rc = lower_step(p, d.steps[t], live, ls);
+    if (rc != CTN_OK) return rc;
+    if (p.slots[ls.out_slot].numel == 0) return CTN_ERR_UNSUPPORTED;  // empty tensors
+    p.flops += ls.flops;
+    if (fuse && ls.elementwise && !lowered.empty() && lowered.back().elementwise &&
+        !lowered.back().tiny && !ls.tiny) {
+      // does this step consume the previous step's output?
+      LoweredStep& prev = lowered.back();
+      auto it = std::find(ls.in_slots.begin(), ls.in_slots.end(), prev.out_slot);
+      size_t merged = prev.in_slots.size() + ls.in_slots.size() - 1;
+      if (it != ls.in_slots.end() && merged <= (size_t)kChainMaxIn) {
+        for (auto s : ls.in_slots)
+          if (s != prev.out_slot) prev.in_slots.push_back(s);
+        prev.out_slot = ls.out_slot;
+        prev.flops += ls.flops;
+        continue;
+      }
+    }
+    lowered.push_back(std::move(ls));
+  }
+  if (live.size() != 1) return CTN_ERR_INVALID;  // the list must reduce to one tensor
+  p.final_slot = live[0];
+  p.slots[p.final_slot].is_final = true;
+
+  // emit device steps + launches, placing intermediates in the arena
+  Arena arena;
+  const bool allow_interp = !(d.flags & CTN_PLAN_NO_INTERPRETER);
+  const bool allow_gemm = !(d.flags & CTN_PLAN_NO_GEMM);
+  for (size_t t = 0; t < lowered.size(); ++t) {
+    LoweredStep& ls = lowered[t];
+    StepDev sd{};
+    sd.n_in = (int32_t)ls.in_slots.size();
+    sd.out_slot = ls.out_slot;
+    sd.out_numel = ls.out_numel;
+    sd.k_numel = ls.k_numel;
+    sd.gemm_off = -1;
+    sd.is_final = ls.out_slot == p.final_slot;
+    sd.ticket = p.n_tickets++;
+    int64_t bytes = p.slots[ls.out_slot].numel;
+    for (auto s : ls.in_slots) bytes += p.slots[s].numel;
+    bytes *= (int64_t)p.elem;
+    const bool big_elementwise = ls.elementwise && !(ls.tiny && allow_interp);
+    if (big_elementwise) {
+      sd.kind = kChain;
+      sd.slot_off = (int32_t)p.slot_list.size();
+      p.slot_list.insert(p.slot_list.end(), ls.in_slots.begin(), ls.in_slots.end());
+      sd.tracked = sd.n_in > 2;
+    } else {
+      for (int i = 0; i < sd.n_in; ++i) sd.in_slot[i] = ls.in_slots[i];
+      sd.n_out_modes = (int32_t)ls.out_modes.size();
+      sd.n_k_modes = (int32_t)ls.k_modes.size();
+      sd.mode_off = (int32_t)p.modes.size();
+      p.modes.insert(p.modes.end(), ls.out_modes.begin(), ls.out_modes.end());
+      p.modes.insert(p.modes.end(), ls.k_modes.begin(), ls.k_modes.end());
+      sd.kind = (ls.tiny && allow_interp) ? kInterp : kGeneric;
+      if (sd.kind == kGeneric && allow_gemm && ls.has_gemm) {
+        sd.gemm_off = (int32_t)p.gemms.size();
+        p.gemms.push_back(ls.gemm);
+        if (gemm_supported(p, sd, ls.gemm)) sd.kind = kGemm;
+        else { p.gemms.pop_back(); sd.gemm_off = -1; }
+      }
+    }
+    // place the output, then release the inputs (never alias within a step)
+    Slot& out = p.slots[ls.out_slot];
+    if (!out.is_final) out.ws_offset = (int64_t)arena.alloc((size_t)out.numel * p.elem);
+    size_t scratch_bytes = 0;
+    if (sd.kind == kChain && sd.tracked) {
+      // one exponent per tile of the chain output (tile = 1024 f64 / 2048 f32 at most;
+      // sized for the smallest tile the kernel variants use)
+      scratch_bytes = (size_t)((out.numel + 511) / 512 + 1) * sizeof(int32_t);
+      sd.scratch_off = (int64_t)arena.alloc(scratch_bytes);
+    }
+    for (auto s : ls.in_slots) {
+      Slot& in = p.slots[s];
+      if (in.operand < 0 && in.ws_offset >= 0) arena.release((size_t)in.ws_offset, (size_t)in.numel * p.elem);
+    }
+    if (scratch_bytes) arena.release((size_t)sd.scratch_off, scratch_bytes);
+    int32_t idx = (int32_t)p.steps.size();
+    p.steps.push_back(sd);
+    if (sd.kind == kInterp && !p.launches.empty() && p.launches.back().kind == kInterp) {
+      p.launches.back().last_step = idx;
+      p.launches.back().bytes += bytes;
+      p.launches.back().flops += ls.flops;
+    } else {
+      p.launches.push_back(Launch{sd.kind, idx, idx, bytes, ls.flops});
+      if (sd.kind == kChain && sd.tracked)
+        p.launches.push_back(Launch{kMaterialize, idx, idx, 2 * out.numel * (int64_t)p.elem, 0.0});
+    }
+  }
+  // the last launch must leave the canonical (T/mean|T|, log-scale) pair:
+  // interpreter and tracked-chain launches do it themselves, others need a pass
+  const Launch& last = p.launches.back();
+  const StepDev& last_step = p.steps[last.last_step];
+  (void)last_step;
+  bool self_final = last.kind == kInterp || last.kind == kMaterialize;
+  if (!self_final) {
+    int64_t bytes = 2 * p.slots[p.final_slot].numel * (int64_t)p.elem;
+    p.launches.push_back(Launch{kFinalize, last.last_step, last.last_step, bytes, 0.0});
+  }
+  p.arena_bytes = arena.top;
+  layout_state(p);
+  return CTN_OK;
+}
+
+static int upload_plan(Plan& p) {
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    // no device: the plan is still usable for introspection (CPU build checks)
+    cudaGetLastError();
+    p.device = -1;
+    return CTN_OK;
+  }
+  CTN_CUDA(cudaGetDevice(&p.device));
+  cudaDeviceProp prop;
+  CTN_CUDA(cudaGetDeviceProperties(&prop, p.device));
+  p.sm_count = prop.multiProcessorCount;
+  auto up = [](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) { *dst = nullptr; return cudaSuccess; }
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  CTN_CUDA(up((void**)&p.d_steps, p.steps.data(), p.steps.size() * sizeof(StepDev)));
+  CTN_CUDA(up((void**)&p.d_modes, p.modes.data(), p.modes.size() * sizeof(ModeDev)));
+  CTN_CUDA(up((void**)&p.d_gemms, p.gemms.data(), p.gemms.size() * sizeof(GemmDev)));
+  CTN_CUDA(up((void**)&p.d_slot_list, p.slot_list.data(), p.slot_list.size() * sizeof(int32_t)));
+  return CTN_OK;
+}
+
+}  // namespace ctn
+
+using namespace ctn;
+
+struct ctn_plan {
+  Plan p;
+};
+
+extern "C" {
+
+int ctn_abi_version(void) { return CTN_ABI_VERSION; }
+
+int ctn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+const char* ctn_status_string(int status) {
+  switch (status) {
+    case CTN_OK: return "ok";
+    case CTN_ERR_INVALID: return "invalid plan description";
+    case CTN_ERR_SHAPE: return "extents of a shared index disagree";
+    case CTN_ERR_UNSUPPORTED: return "contraction not supported by the B200 engine";
+    case CTN_ERR_CUDA: return "CUDA error";
+    case CTN_ERR_NOMEM: return "out of memory";
+    case CTN_ERR_NO_DEVICE: return "no sm_100 CUDA device available";
+    default: return "unknown status";
+  }
+}
+
+const char* ctn_last_cuda_error(void) { return g_cuda_error.c_str(); }
+
+int ctn_plan_create(const ctn_plan_desc* desc, ctn_plan** plan_out) {
+  if (!desc || !plan_out) return CTN_ERR_INVALID;
+  ctn_plan* h = new (std::nothrow) ctn_plan();
+  if (!h) return CTN_ERR_NOMEM;
+  int rc;
+  try {
+    rc = build_plan(*desc, h->p);
+    if (rc == CTN_OK) rc = upload_plan(h->p);
+  } catch (const std::bad_alloc&) {
+    rc = CTN_ERR_NOMEM;
+  } catch (...) {
+    rc = CTN_ERR_INVALID;
+  }
+  if (rc != CTN_OK) {
+    ctn_plan_destroy(h);
+    return rc;
+  }
+  *plan_out = h;
+  return CTN_OK;
+}
+
+void ctn_plan_destroy(ctn_plan* plan) {
+  if (!plan) return;
+  Plan& p = plan->p;
+  if (p.device >= 0) {
+    cudaFree(p.d_steps);
+    cudaFree(p.d_modes);
+    cudaFree(p.d_gemms);
+    cudaFree(p.d_slot_list);
+    cudaFree(p.h_ws);
+    cudaFree(p.h_out);
+    cudaFree(p.h_log);
+    std::set<void*> freed;
+    for (void* q : p.h_operands)
+      if (q && freed.insert(q).second) cudaFree(q);
+  }
+  delete plan;
+}
+
+size_t ctn_plan_workspace_bytes(const ctn_plan* plan) {
+  if (!plan) return 0;
+  return plan->p.state.total + align_up(plan->p.arena_bytes, 256) + 256;
+}
+
+int ctn_plan_output_rank(const ctn_plan* plan) {
+  return plan ? (int)plan->p.slots[plan->p.final_slot].extents.size() : -1;
+}
+
+int ctn_plan_output_extents(const ctn_plan* plan, int64_t* extents) {
+  if (!plan) return CTN_ERR_INVALID;
+  const Slot& s = plan->p.slots[plan->p.final_slot];
+  if (extents)
+    for (size_t i = 0; i < s.extents.size(); ++i) extents[i] = s.extents[i];
+  return CTN_OK;
+}
+
+int64_t ctn_plan_output_numel(const ctn_plan* plan) {
+  return plan ? plan->p.slots[plan->p.final_slot].numel : -1;
+}
+
+int ctn_plan_num_launches(const ctn_plan* plan) {
+  if (!plan) return -1;
+  return (int)plan->p.launches.size();
+}
+
+double ctn_plan_flops(const ctn_plan* plan) { return plan ? plan->p.flops : 0.0; }
+
+double ctn_plan_step_bytes(const ctn_plan* plan) {
+  if (!plan) return 0.0;
+  double b = 0;
+  for (auto& l : plan->p.launches)
+    if (l.kind != kFinalize && l.kind != kMaterialize) b += (double)l.bytes;
+  return b;
+}
+
+int ctn_plan_launch_kind(const ctn_plan* plan, int i) {
+  if (!plan || i < 0 || i >= (int)plan->p.launches.size()) return -1;
+  return plan->p.launches[i].kind;
+}
+
+static int execute_impl(const ctn_plan* plan, const void* const* operands, void* out, double* log_scale_out,
+                        int32_t* flags_out, void* workspace, int out_mode, void* stream_, cudaEvent_t* events) {
+  if (!plan || !operands || !out || !log_scale_out || !workspace) return CTN_ERR_INVALID;
+  if (out_mode != CTN_OUT_SPLIT && out_mode != CTN_OUT_DENSE) return CTN_ERR_INVALID;
+  const Plan& p = plan->p;
+  if (p.device < 0) return CTN_ERR_NO_DEVICE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  if (((uintptr_t)ws & 255) != 0) return CTN_ERR_INVALID;
+
+  // (re)initialise the state block: log-scale 0, every pending scale 1,
+  // arrival counters 0, and the slot -> device pointer table
+  const StateLayout& st = p.state;
+  static thread_local std::vector<char> image;
+  image.assign(st.init_bytes, 0);
+  double* inv = (double*)(image.data() + st.inv_kappa);
+  double* kap = (double*)(image.data() + st.kappa);
+  void** ptrs = (void**)(image.data() + st.ptrs);
+  char* arena = ws + st.total;
+  for (size_t i = 0; i < p.slots.size(); ++i) {
+    inv[i] = 1.0;
+    kap[i] = 1.0;
+    const Slot& s = p.slots[i];
+    if (s.operand >= 0) ptrs[i] = (void*)operands[s.operand];
+    else if (s.is_final) ptrs[i] = out;
+    else if (s.ws_offset >= 0) ptrs[i] = arena + s.ws_offset;
+    else ptrs[i] = nullptr;  // fused away
+    if (s.operand >= 0 && !ptrs[i]) return CTN_ERR_INVALID;
+  }
+  CTN_CUDA(cudaMemcpyAsync(ws, image.data(), st.init_bytes, cudaMemcpyHostToDevice, stream));
+
+  ExecCtx ctx{&p, ws, stream, out_mode, log_scale_out, flags_out};
+  auto chain_vec_ok = [&](const StepDev& s) {
+    bool ok = ((uintptr_t)ptrs[s.out_slot] & 15) == 0;
+    for (int i = 0; i < s.n_in; ++i) ok = ok && (((uintptr_t)ptrs[p.slot_list[s.slot_off + i]] & 15) == 0);
+    return ok;
+  };
+  for (size_t li = 0; li < p.launches.size(); ++li) {
+    const Launch& l = p.launches[li];
+    if (events) CTN_CUDA(cudaEventRecord(events[li], stream));
+    cudaError_t e = cudaSuccess;
+    switch (l.kind) {
+      case kGeneric: e = launch_generic(ctx, l); break;
+      case kChain: e = launch_chain(ctx, l, chain_vec_ok(p.steps[l.first_step])); break;
+      case kMaterialize: e = launch_materialize(ctx, l, chain_vec_ok(p.steps[l.first_step])); break;
+      case kInterp: e = launch_interp(ctx, l); break;
+      case kGemm: e = launch_gemm(ctx, l); break;
+      case kFinalize: e = launch_finalize(ctx, l); break;
+      default: return CTN_ERR_INVALID;
+    }
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "kernel launch");
+      return CTN_ERR_CUDA;
+    }
+  }
+  if (events) CTN_CUDA(cudaEventRecord(events[p.launches.size()], stream));
+  return CTN_OK;
+}
+
+int ctn_plan_execute(const ctn_plan* plan, const void* const* operands, void* out, double* log_scale_out,
+                     int32_t* flags_out, void* workspace, int out_mode, void* stream_) {
+  return execute_impl(plan, operands, out, log_scale_out, flags_out, workspace, out_mode, stream_, nullptr);
+}
+
+int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, void* out, double* log_scale_out,
+                           int32_t* flags_out, void* workspace, int out_mode, void* stream_, float* launch_ms) {
+  if (!plan || !launch_ms) return CTN_ERR_INVALID;
+  const size_t n = plan->p.launches.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CTN_CUDA(cudaEventCreate(&e));
+  int rc = execute_impl(plan, operands, out, log_scale_out, flags_out, workspace, out_mode, stream_, ev.data());
+  if (rc == CTN_OK) {
+    cudaError_t e = cudaEventSynchronize(ev[n]);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaEventSynchronize"); rc = CTN_ERR_CUDA; }
+    for (size_t i = 0; rc == CTN_OK && i < n; ++i) cudaEventElapsedTime(&launch_ms[i], ev[i], ev[i + 1]);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void* out_host,
+                          double* log_scale_host, int32_t* flags_host, int out_mode) {
+  if (!plan || !operands_host || !out_host || !log_scale_host) return CTN_ERR_INVALID;
+  Plan& p = plan->p;
+  if (p.device < 0) return CTN_ERR_NO_DEVICE;
+  CTN_CUDA(cudaSetDevice(p.device));
+  size_t ws_bytes = ctn_plan_workspace_bytes(plan);
+  if (!p.h_ws) {
+    CTN_CUDA(cudaMalloc(&p.h_ws, ws_bytes));
+    p.h_ws_bytes = ws_bytes;
+    CTN_CUDA(cudaMalloc(&p.h_out, std::max<size_t>(16, (size_t)p.slots[p.final_slot].numel * p.elem)));
+    CTN_CUDA(cudaMalloc((void**)&p.h_log, 16));
+    p.h_operands.assign(p.n_operands, nullptr);
+    p.h_operand_bytes.assign(p.n_operands, 0);
+    for (int i = 0; i < p.n_operands; ++i) {
+      const Slot& s = p.slots[i];
+      size_t span = 1;
+      for (size_t a = 0; a < s.extents.size(); ++a) span += (size_t)(s.extents[a] - 1) * (size_t)s.strides[a];
+      p.h_operand_bytes[i] = span * p.elem;
+    }
+  }
+  // the same host array passed for several operands (weight sharing) is
+  // uploaded once
+  std::map<const void*, int> first_use;
+  std::vector<const void*> dev(p.n_operands);
+  for (int i = 0; i < p.n_operands; ++i) {
+    if (!operands_host[i]) return CTN_ERR_INVALID;
+    auto it = first_use.find(operands_host[i]);
+    if (it != first_use.end() && p.h_operand_bytes[it->second] >= p.h_operand_bytes[i]) {
+      dev[i] = dev[it->second];
+      continue;
+    }
+    if (!p.h_operands[i]) CTN_CUDA(cudaMalloc(&p.h_operands[i], std::max<size_t>(16, p.h_operand_bytes[i])));
+    CTN_CUDA(cudaMemcpyAsync(p.h_operands[i], operands_host[i], p.h_operand_bytes[i], cudaMemcpyHostToDevice, 0));
+    dev[i] = p.h_operands[i];
+    first_use[operands_host[i]] = i;
+  }
+  int rc = ctn_plan_execute(plan, dev.data(), p.h_out, p.h_log, (int32_t*)(p.h_log + 1), p.h_ws, out_mode, nullptr);
+  if (rc != CTN_OK) return rc;
+  CTN_CUDA(cudaMemcpyAsync(out_host, p.h_out, (size_t)p.slots[p.final_slot].numel * p.elem, cudaMemcpyDeviceToHost, 0));
+  double tail[2] = {0, 0};
+  CTN_CUDA(cudaMemcpyAsync(tail, p.h_log, 16, cudaMemcpyDeviceToHost, 0));
+  CTN_CUDA(cudaStreamSynchronize(0));
+  *log_scale_host = tail[0];
+  if (flags_host) memcpy(flags_host, &tail[1], sizeof(int32_t));
+  return CTN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,459 @@
+"""Python host side of the B200 contraction engine.
+
+Mirrors the reference's contraction front end and executor for the one hot path
+(`/root/reference/contractn/einsum.py`):
+
+* :func:`contract`       -- same signature and keyword handling as
+  ``contract`` (einsum.py:190-310).
+* :func:`core_contract`  -- same signature as ``_core_contract``
+  (einsum.py:326-393); this is the seam :func:`install` patches into an
+  importable reference package (seam B).
+* :class:`Plan`          -- a compiled contraction list living on the device
+  (thin ctypes wrapper over ``include/ctn_b200.h``).
+
+All arithmetic runs in ``libctn_b200.so`` (hand-written sm_100a kernels).  There
+is NO CPU fallback: if the library or a B200 is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from collections import OrderedDict
+
+import numpy as np
+
+from . import planner
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libctn_b200.so")
+
+CTN_F32, CTN_F64 = 0, 1
+CTN_OUT_SPLIT, CTN_OUT_DENSE = 0, 1
+CTN_PLAN_EXACT_STEPS = 1
+CTN_PLAN_NO_INTERPRETER = 2
+CTN_PLAN_NO_GEMM = 4
+CTN_RESULT_DEGENERATE = 1
+LAUNCH_KINDS = ("generic", "chain", "interp", "gemm", "finalize", "materialize")
+
+EXPORTS = (
+    "ctn_plan_create", "ctn_plan_destroy", "ctn_plan_workspace_bytes",
+    "ctn_plan_output_rank", "ctn_plan_output_extents", "ctn_plan_output_numel",
+    "ctn_plan_num_launches", "ctn_plan_flops", "ctn_plan_step_bytes",
+    "ctn_plan_launch_kind", "ctn_plan_execute", "ctn_plan_execute_timed", "ctn_plan_execute_host",
+    "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
+)
+
+
+class EngineError(RuntimeError):
+    """A call into libctn_b200 failed (status and CUDA error text attached)."""
+
+
+class _StepDesc(ctypes.Structure):
+    _fields_ = [
+        ("n_inputs", ctypes.c_int32),
+        ("positions", ctypes.POINTER(ctypes.c_int32)),
+        ("input_ranks", ctypes.POINTER(ctypes.c_int32)),
+        ("input_labels", ctypes.POINTER(ctypes.c_int32)),
+        ("out_rank", ctypes.c_int32),
+        ("out_labels", ctypes.POINTER(ctypes.c_int32)),
+    ]
+
+
+class _PlanDesc(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
+        ("n_operands", ctypes.c_int32),
+        ("operand_ranks", ctypes.POINTER(ctypes.c_int32)),
+        ("operand_extents", ctypes.POINTER(ctypes.c_int64)),
+        ("operand_strides", ctypes.POINTER(ctypes.c_int64)),
+        ("n_steps", ctypes.c_int32),
+        ("steps", ctypes.POINTER(_StepDesc)),
+        ("flags", ctypes.c_int32),
+    ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen ``libctn_b200.so`` (building it first if the sources are newer)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            from .build import build_library
+
+            build_library()
+        lib = ctypes.CDLL(_LIB_PATH)
+        vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+        lib.ctn_plan_create.argtypes = [ctypes.POINTER(_PlanDesc), ctypes.POINTER(vp)]
+        lib.ctn_plan_create.restype = ctypes.c_int
+        lib.ctn_plan_destroy.argtypes = [vp]
+        lib.ctn_plan_destroy.restype = None
+        lib.ctn_plan_workspace_bytes.argtypes = [vp]
+        lib.ctn_plan_workspace_bytes.restype = ctypes.c_size_t
+        lib.ctn_plan_output_rank.argtypes = [vp]
+        lib.ctn_plan_output_rank.restype = ctypes.c_int
+        lib.ctn_plan_output_extents.argtypes = [vp, ctypes.POINTER(i64)]
+        lib.ctn_plan_output_extents.restype = ctypes.c_int
+        lib.ctn_plan_output_numel.argtypes = [vp]
+        lib.ctn_plan_output_numel.restype = i64
+        lib.ctn_plan_num_launches.argtypes = [vp]
+        lib.ctn_plan_num_launches.restype = ctypes.c_int
+        lib.ctn_plan_flops.argtypes = [vp]
+        lib.ctn_plan_flops.restype = dbl
+        lib.ctn_plan_step_bytes.argtypes = [vp]
+        lib.ctn_plan_step_bytes.restype = dbl
+        lib.ctn_plan_launch_kind.argtypes = [vp, ctypes.c_int]
+        lib.ctn_plan_launch_kind.restype = ctypes.c_int
+        lib.ctn_plan_execute.argtypes = [vp, ctypes.POINTER(vp), vp, vp, vp, vp, ctypes.c_int, vp]
+        lib.ctn_plan_execute.restype = ctypes.c_int
+        lib.ctn_plan_execute_timed.argtypes = [vp, ctypes.POINTER(vp), vp, vp, vp, vp, ctypes.c_int, vp,
+                                               ctypes.POINTER(ctypes.c_float)]
+        lib.ctn_plan_execute_timed.restype = ctypes.c_int
+        lib.ctn_plan_execute_host.argtypes = [vp, ctypes.POINTER(vp), vp, ctypes.POINTER(dbl),
+                                              ctypes.POINTER(i32), ctypes.c_int]
+        lib.ctn_plan_execute_host.restype = ctypes.c_int
+        lib.ctn_status_string.argtypes = [ctypes.c_int]
+        lib.ctn_status_string.restype = ctypes.c_char_p
+        lib.ctn_last_cuda_error.argtypes = []
+        lib.ctn_last_cuda_error.restype = ctypes.c_char_p
+        lib.ctn_abi_version.restype = ctypes.c_int
+        lib.ctn_device_count.restype = ctypes.c_int
+        _lib = lib
+        return lib
+
+
+def _check(status, what):
+    if status != 0:
+        lib = load_library()
+        msg = lib.ctn_status_string(status).decode()
+        cuda = lib.ctn_last_cuda_error().decode()
+        raise EngineError(f"{what}: {msg}" + (f" [{cuda}]" if cuda and status == 4 else ""))
+
+
+def _i32(seq):
+    return (ctypes.c_int32 * max(1, len(seq)))(*seq)
+
+
+def _i64(seq):
+    return (ctypes.c_int64 * max(1, len(seq)))(*seq)
+
+
+class Plan:
+    """A contraction list compiled for the device (``ctn_plan`` handle).
+
+    ``contraction_list`` is what ``contract_path(..., einsum_call=True)`` returns
+    (einsum.py:341-342); ``shapes``/``strides`` (elements, ``None`` for
+    C-contiguous) describe the operands; ``dtype`` is ``np.float32``/``np.float64``.
+    """
+
+    def __init__(self, contraction_list, shapes, dtype, strides=None, flags=0):
+        lib = load_library()
+        self._lib = lib
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise NotImplementedError(f"dtype {self.dtype} is not supported by the B200 engine")
+        self.shapes = tuple(tuple(int(d) for d in s) for s in shapes)
+        keep = []  # ctypes arrays must outlive ctn_plan_create
+        steps = (_StepDesc * len(contraction_list))()
+        for t, (positions, _removed, einsum_str, _rem, _flag) in enumerate(contraction_list):
+            ins, out = einsum_str.split("->")
+            terms = ins.split(",")
+            if len(terms) != len(positions):
+                raise ValueError(f"step {t}: {len(positions)} positions for '{einsum_str}'")
+            pos = _i32(list(positions))
+            ranks = _i32([len(x) for x in terms])
+            labels = _i32([ord(ch) for term in terms for ch in term])
+            outl = _i32([ord(ch) for ch in out])
+            keep += [pos, ranks, labels, outl]
+            steps[t].n_inputs = len(terms)
+            steps[t].positions = pos
+            steps[t].input_ranks = ranks
+            steps[t].input_labels = labels
+            steps[t].out_rank = len(out)
+            steps[t].out_labels = outl
+        desc = _PlanDesc()
+        desc.abi_version = 1
+        desc.dtype = CTN_F32 if self.dtype == np.float32 else CTN_F64
+        desc.n_operands = len(self.shapes)
+        ranks = _i32([len(s) for s in self.shapes])
+        extents = _i64([d for s in self.shapes for d in s])
+        desc.operand_ranks = ranks
+        desc.operand_extents = extents
+        if strides is not None:
+            strd = _i64([int(v) for s in strides for v in s])
+            desc.operand_strides = strd
+            keep.append(strd)
+        desc.n_steps = len(contraction_list)
+        desc.steps = steps
+        desc.flags = flags
+        handle = ctypes.c_void_p()
+        _check(lib.ctn_plan_create(ctypes.byref(desc), ctypes.byref(handle)), "ctn_plan_create")
+        self._h = handle
+        self.flags = flags
+        rank = lib.ctn_plan_output_rank(handle)
+        ext = (ctypes.c_int64 * max(1, rank))()
+        _check(lib.ctn_plan_output_extents(handle, ext), "ctn_plan_output_extents")
+        self.out_shape = tuple(int(ext[i]) for i in range(rank))
+        self.workspace_bytes = int(lib.ctn_plan_workspace_bytes(handle))
+        self.num_launches = int(lib.ctn_plan_num_launches(handle))
+        self.flops = float(lib.ctn_plan_flops(handle))
+        self.step_bytes = float(lib.ctn_plan_step_bytes(handle))
+        kinds = []
+        i = 0
+        while True:
+            k = lib.ctn_plan_launch_kind(handle, i)
+            if k < 0:
+                break
+            kinds.append(LAUNCH_KINDS[k])
+            i += 1
+        self.launch_kinds = tuple(kinds)
+        self._dev = None  # torch scratch for the device path
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and self._lib is not None:
+            try:
+                self._lib.ctn_plan_destroy(h)
+            except Exception:
+                pass
+
+    # -- host buffers in, host buffers out ---------------------------------
+    def execute_host(self, arrays, out_mode=CTN_OUT_SPLIT):
+        """Run on host ``numpy`` arrays (copies in and out).  Returns
+        ``(result, log_scale, flags)``."""
+        n = len(self.shapes)
+        assert len(arrays) == n
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        out = np.empty(self.out_shape, dtype=self.dtype)
+        log_scale = ctypes.c_double(0.0)
+        flags = ctypes.c_int32(0)
+        _check(
+            self._lib.ctn_plan_execute_host(self._h, ptrs, out.ctypes.data, ctypes.byref(log_scale),
+                                            ctypes.byref(flags), out_mode),
+            "ctn_plan_execute_host",
+        )
+        return out, log_scale.value, flags.value
+
+    # -- device buffers (torch CUDA tensors or raw pointers) ----------------
+    def _device_scratch(self, device):
+        import torch
+
+        if self._dev is None or self._dev[0] != device:
+            ws = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8, device=device)
+            base = ws.data_ptr()
+            pad = (-base) % 256
+            tail = torch.zeros(2, dtype=torch.float64, device=device)  # [log_scale, flags bits]
+            self._dev = (device, ws, base + pad, tail)
+        return self._dev
+
+    def execute_device(self, tensors, out=None, out_mode=CTN_OUT_SPLIT, stream=None, timed=False):
+        """Run on torch CUDA tensors without leaving the device.  Returns
+        ``(out, tail)`` where ``tail[0]`` is the log-scale (float64, on device) and
+        ``tail[1]`` reinterpreted as int32 holds the result flags.  With
+        ``timed=True`` returns ``(out, tail, [ms per kernel])`` (synchronises)."""
+        import torch
+
+        device = tensors[0].device
+        _, _ws, ws_ptr, tail = self._device_scratch(device)
+        tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
+        if out is None:
+            out = torch.empty(self.out_shape, dtype=tdtype, device=device)
+        n = len(self.shapes)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        if stream is None:
+            stream = torch.cuda.current_stream(device).cuda_stream
+        if timed:
+            ms = (ctypes.c_float * max(1, self.num_launches))()
+            _check(
+                self._lib.ctn_plan_execute_timed(self._h, ptrs, out.data_ptr(), tail.data_ptr(),
+                                                 tail.data_ptr() + 8, ws_ptr, out_mode, stream, ms),
+                "ctn_plan_execute_timed",
+            )
+            return out, tail, [float(ms[i]) for i in range(self.num_launches)]
+        _check(
+            self._lib.ctn_plan_execute(self._h, ptrs, out.data_ptr(), tail.data_ptr(), tail.data_ptr() + 8,
+                                       ws_ptr, out_mode, stream),
+            "ctn_plan_execute",
+        )
+        return out, tail
+
+    @property
+    def may_degenerate(self):
+        return "chain" in self.launch_kinds and not (self.flags & CTN_PLAN_EXACT_STEPS)
+
+
+# ---------------------------------------------------------------------------
+# plan cache (plays the role of the lru_cache on _contract_path, einsum.py:313)
+# ---------------------------------------------------------------------------
+_plan_cache = OrderedDict()
+_PLAN_CACHE_SIZE = 128
+
+
+def _hashable_list(contraction_list):
+    return tuple((tuple(c[0]), c[2]) for c in contraction_list)
+
+
+def get_plan(contraction_list, shapes, dtype, strides=None, flags=0):
+    key = (_hashable_list(contraction_list), tuple(shapes), np.dtype(dtype).str,
+           None if strides is None else tuple(strides), flags)
+    plan = _plan_cache.get(key)
+    if plan is None:
+        plan = Plan(contraction_list, shapes, dtype, strides=strides, flags=flags)
+        _plan_cache[key] = plan
+        if len(_plan_cache) > _PLAN_CACHE_SIZE:
+            _plan_cache.popitem(last=False)
+    else:
+        _plan_cache.move_to_end(key)
+    return plan
+
+
+def clear_plan_cache():
+    _plan_cache.clear()
+
+
+# ---------------------------------------------------------------------------
+# operand handling
+# ---------------------------------------------------------------------------
+def _is_torch(x):
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def _compute_dtype(dtypes):
+    kinds = {np.dtype(d).kind for d in dtypes}
+    if "c" in kinds:
+        raise NotImplementedError("complex tensors are not supported by the B200 engine")
+    res = np.result_type(*dtypes) if dtypes else np.dtype(np.float64)
+    if res == np.float32 or res == np.float16:
+        return np.dtype(np.float32)
+    return np.dtype(np.float64)
+
+
+def _prep_numpy(op, dtype):
+    a = np.asarray(op)
+    if a.dtype != dtype:
+        a = a.astype(dtype)
+    item = a.dtype.itemsize
+    if any(s < 0 or s % item for s in a.strides):
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def _elem_strides(a):
+    item = a.dtype.itemsize
+    return tuple(int(s // item) for s in a.strides)
+
+
+def _run_numpy(arrays, contraction_list):
+    dtype = _compute_dtype([np.asarray(a).dtype for a in arrays])
+    arrays = [_prep_numpy(a, dtype) for a in arrays]
+    shapes = tuple(a.shape for a in arrays)
+    strides = tuple(_elem_strides(a) for a in arrays)
+    plan = get_plan(contraction_list, shapes, dtype, strides=strides)
+    out, log_scale, flags = plan.execute_host(arrays)
+    if flags & CTN_RESULT_DEGENERATE:
+        exact = get_plan(contraction_list, shapes, dtype, strides=strides, flags=CTN_PLAN_EXACT_STEPS)
+        out, log_scale, flags = exact.execute_host(arrays)
+    return out, np.array(log_scale, dtype=np.float64)
+
+
+def _run_torch(tensors, contraction_list, dense=False):
+    import torch
+
+    if not tensors[0].is_cuda:
+        out, log_scale = _run_numpy([t.detach().numpy() for t in tensors], contraction_list)
+        res = torch.from_numpy(np.ascontiguousarray(out))
+        return res, torch.tensor(float(log_scale), dtype=res.dtype)
+    tdt = torch.float64 if any(t.dtype == torch.float64 for t in tensors) else torch.float32
+    if any(t.is_complex() for t in tensors):
+        raise NotImplementedError("complex tensors are not supported by the B200 engine")
+    tensors = [t.detach().to(tdt) for t in tensors]
+    tensors = [t if all(s >= 0 for s in t.stride()) else t.contiguous() for t in tensors]
+    shapes = tuple(tuple(t.shape) for t in tensors)
+    strides = tuple(tuple(t.stride()) for t in tensors)
+    ndt = np.float64 if tdt == torch.float64 else np.float32
+    plan = get_plan(contraction_list, shapes, ndt, strides=strides)
+    out, tail = plan.execute_device(tensors)
+    if plan.may_degenerate:
+        flags = int(tail[1:2].view(torch.int32)[0].item())
+        if flags & CTN_RESULT_DEGENERATE:
+            exact = get_plan(contraction_list, shapes, ndt, strides=strides, flags=CTN_PLAN_EXACT_STEPS)
+            out, tail = exact.execute_device(tensors)
+    return out, tail[0].clone().to(tdt)
+
+
+def core_contract(operands, contract_list, backend=None, **einsum_kwargs):
+    """Drop-in for ``_core_contract`` (einsum.py:326-393): ``(tensor, log_scale)``.
+
+    ``operands`` are borrowed and never modified.  ``backend`` is accepted for
+    signature compatibility; the result lives where the operands live (numpy in ->
+    numpy out, torch CUDA in -> torch CUDA out).
+    """
+    operands = list(operands)
+    if einsum_kwargs.get("dtype") is not None:
+        operands = [np.asarray(o, dtype=einsum_kwargs["dtype"]) for o in operands]
+    if _is_torch(operands[0]):
+        return _run_torch(operands, contract_list)
+    return _run_numpy(operands, contract_list)
+
+
+def contract(*operands, **kwargs):
+    """Stabilised einsum on the B200: mirror of ``contract`` (einsum.py:190-310).
+
+    ``contract(einstr, *operands, optimize="auto", split_format=False,
+    memory_limit=None, use_blas=True, backend="auto", dtype=, order=, casting=)``
+    """
+    optimize_arg = kwargs.pop("optimize", True)
+    if optimize_arg is True:
+        optimize_arg = "auto"
+    valid_einsum_kwargs = ("dtype", "order", "casting")
+    einsum_kwargs = {k: v for k, v in kwargs.items() if k in valid_einsum_kwargs}
+    use_blas = kwargs.pop("use_blas", True)
+    split_format = kwargs.pop("split_format", False)
+    memory_limit = kwargs.pop("memory_limit", None)
+    kwargs.pop("backend", "auto")
+    unknown = [k for k in kwargs if k not in valid_einsum_kwargs]
+    if unknown:
+        raise TypeError("Did not understand the following kwargs: {}".format(unknown))
+
+    assert isinstance(operands[0], str)
+    einstr, ops = operands[0], operands[1:]
+    shapes = tuple(tuple(op.shape) for op in ops)
+    contract_list = planner.cached_contract_list(
+        einstr, shapes, optimize=optimize_arg, memory_limit=memory_limit, use_blas=use_blas
+    )
+    result, log_scale = core_contract(ops, contract_list, **einsum_kwargs)
+    if split_format:
+        return result, log_scale
+    # destabilize (einsum.py:110-114) with the operands' own array library
+    if _is_torch(result):
+        import torch
+
+        return result * torch.exp(log_scale)
+    with np.errstate(over="ignore"):
+        return result * np.exp(log_scale)
+
+
+def install(contractn_module=None):
+    """Patch an importable reference package so that ``TN.contract`` runs on the
+    B200 (seam B: replaces ``contractn.einsum._core_contract``).  Returns the
+    original function so the caller can restore it."""
+    if contractn_module is None:
+        import contractn as contractn_module
+    ein = contractn_module.einsum
+    original = ein._core_contract
+    ein._core_contract = core_contract
+    return original
+
+
+def device_available():
+    """True when the library loads and sees at least one compute-10.x device."""
+    try:
+        return load_library().ctn_device_count() > 0
+    except Exception:
+        return False

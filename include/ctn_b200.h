@@ -1,0 +1,168 @@
+/*
+ * ctn_b200.h -- C ABI of the B200-native contraction engine for ContracTN.
+ *
+ * This is the drop-in boundary for ONE path of jemisjoky/ContracTN: the
+ * stabilised pairwise contraction executor
+ *
+ *     _core_contract(operands, contract_list, backend)  contractn/einsum.py:326-393
+ *     stabilize(tensor, log_scale, backend)             contractn/einsum.py:89-107
+ *     destabilize(tensor, log_scale, backend)           contractn/einsum.py:110-114
+ *
+ * The reference is pure Python and has no FFI of its own; the entry points
+ * below are what a ctypes binding placed at the `_core_contract` call site
+ * (contractn/einsum.py:303) binds.  INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every function returns an int status
+ *    (CTN_OK == 0) and never throws; ctn_status_string() explains a status.
+ *  - the caller owns every data buffer.  A plan owns only immutable metadata
+ *    (host structs + a device copy of the step descriptors), so one plan may be
+ *    executed concurrently on distinct streams with distinct workspaces.
+ *  - execution is asynchronous on the given stream; no hidden synchronisation
+ *    in ctn_plan_execute().  ctn_plan_execute_host() is synchronous.
+ *  - element strides, not byte strides.  Outputs are C-contiguous in the order
+ *    of the last step's output subscript.
+ *  - index labels are arbitrary non-negative int32 (the host maps einsum
+ *    symbols, which may be any unicode code point, to integers).
+ */
+#ifndef CTN_B200_H
+#define CTN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTN_ABI_VERSION 1
+
+/* status codes */
+enum {
+  CTN_OK = 0,
+  CTN_ERR_INVALID = 1,     /* malformed description (ranks, labels, positions) */
+  CTN_ERR_SHAPE = 2,       /* extents of a shared label disagree                */
+  CTN_ERR_UNSUPPORTED = 3, /* valid but outside what the kernels handle         */
+  CTN_ERR_CUDA = 4,        /* a CUDA runtime call failed; see ctn_last_cuda_error */
+  CTN_ERR_NOMEM = 5,
+  CTN_ERR_NO_DEVICE = 6    /* no sm_100 device visible                          */
+};
+
+/* arithmetic type of the whole plan */
+enum { CTN_F32 = 0, CTN_F64 = 1 };
+
+/* plan flags */
+enum {
+  /* Execute every pairwise step on its own, with the reference's per-step
+   * rescale decisions (contractn/einsum.py:102).  Without it, runs of
+   * same-layout Hadamard steps (copy-node hubs) are fused into one n-ary
+   * kernel; the final (tensor, log-scale) is identical (the per-step rescale is
+   * a gauge) unless a norm on the way is <= 1e-7, which the fused kernel
+   * detects and reports through CTN_RESULT_DEGENERATE. */
+  CTN_PLAN_EXACT_STEPS = 1,
+  /* Disable the single-CTA interpreter for runs of tiny steps. */
+  CTN_PLAN_NO_INTERPRETER = 2,
+  /* Disable the tiled tensor-core GEMM kernels (use the generic kernel). */
+  CTN_PLAN_NO_GEMM = 4
+};
+
+/* output modes of ctn_plan_execute */
+enum {
+  CTN_OUT_SPLIT = 0, /* out = T / mean|T|, *log_scale = running log-scale      */
+  CTN_OUT_DENSE = 1  /* out = (T / mean|T|) * exp(log_scale)  (destabilize)    */
+};
+
+/* result flags written next to the log-scale */
+enum {
+  CTN_RESULT_DEGENERATE = 1 /* a fused step met a norm <= 1e-7 or a non-finite
+                               value: re-run with CTN_PLAN_EXACT_STEPS to get
+                               the reference's exact (tensor, log-scale) pair */
+};
+
+/* One entry of the contraction list (contractn/einsum.py:341-344): the
+ * operands at `positions` (in the order given, i.e. descending) are popped from
+ * the running operand list and their contraction is appended to it. */
+typedef struct {
+  int32_t n_inputs;            /* >= 1; 2 for every pairwise step               */
+  const int32_t* positions;    /* [n_inputs]                                     */
+  const int32_t* input_ranks;  /* [n_inputs] number of subscripts of each input  */
+  const int32_t* input_labels; /* concatenated subscripts of the inputs          */
+  int32_t out_rank;
+  const int32_t* out_labels;   /* [out_rank] output subscript of the step        */
+} ctn_step_desc;
+
+typedef struct {
+  int32_t abi_version;            /* CTN_ABI_VERSION                             */
+  int32_t dtype;                  /* CTN_F32 | CTN_F64                           */
+  int32_t n_operands;
+  const int32_t* operand_ranks;   /* [n_operands]                                */
+  const int64_t* operand_extents; /* concatenated                                */
+  const int64_t* operand_strides; /* concatenated, elements; NULL = C-contiguous */
+  int32_t n_steps;                /* 0 is invalid: a 1-operand network still has
+                                     one step (contractn/einsum.py:341)          */
+  const ctn_step_desc* steps;
+  int32_t flags;                  /* CTN_PLAN_*                                  */
+} ctn_plan_desc;
+
+typedef struct ctn_plan ctn_plan;
+
+/* Build a device-resident plan from a contraction list.  Replaces the Python
+ * loop header of _core_contract (contractn/einsum.py:331-344): operand
+ * bookkeeping, routing (einsum.py:347) and axis computation (einsum.py:357-368)
+ * are resolved here once instead of on every call. */
+int ctn_plan_create(const ctn_plan_desc* desc, ctn_plan** plan_out);
+void ctn_plan_destroy(ctn_plan* plan);
+
+/* Scratch the caller must provide to ctn_plan_execute (intermediates + the
+ * per-execution state block); 256-byte aligned device memory. */
+size_t ctn_plan_workspace_bytes(const ctn_plan* plan);
+
+/* Shape of the result (C-contiguous). `extents` may be NULL to query the rank. */
+int ctn_plan_output_rank(const ctn_plan* plan);
+int ctn_plan_output_extents(const ctn_plan* plan, int64_t* extents);
+int64_t ctn_plan_output_numel(const ctn_plan* plan);
+
+/* Introspection used by the benchmark and the tests. */
+int ctn_plan_num_launches(const ctn_plan* plan);      /* kernels per execute     */
+double ctn_plan_flops(const ctn_plan* plan);          /* path FLOPs, opt_einsum convention */
+double ctn_plan_step_bytes(const ctn_plan* plan);     /* sum over launches of operand+result bytes */
+/* kind of launch i: 0 generic, 1 hadamard-chain, 2 interpreter, 3 gemm, 4 finalize,
+ * 5 chain materialise pass; -1 past the end */
+int ctn_plan_launch_kind(const ctn_plan* plan, int i);
+
+/* Run the plan: the body of _core_contract (contractn/einsum.py:341-393) plus
+ * stabilize after every step (einsum.py:387, 89-107) and, for CTN_OUT_DENSE,
+ * destabilize (einsum.py:310).  All pointers are DEVICE pointers.
+ *   operands      [n_operands] device pointers (borrowed, never written)
+ *   out           output tensor, ctn_plan_output_numel() elements
+ *   log_scale_out one double: the log-scale register (contractn/einsum.py:338)
+ *   flags_out     one int32 of CTN_RESULT_* (may be NULL)
+ *   stream        cudaStream_t (NULL = default stream) */
+int ctn_plan_execute(const ctn_plan* plan, const void* const* operands, void* out,
+                     double* log_scale_out, int32_t* flags_out, void* workspace,
+                     int out_mode, void* stream);
+
+/* ctn_plan_execute with a CUDA event between consecutive kernels; synchronises
+ * the stream and returns each kernel's device time in launch_ms[0 ..
+ * ctn_plan_num_launches()).  Measurement aid for bench.py (per-kernel roofline). */
+int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, void* out,
+                           double* log_scale_out, int32_t* flags_out, void* workspace,
+                           int out_mode, void* stream, float* launch_ms);
+
+/* Same with HOST buffers: copies the operands to the device, runs the plan,
+ * copies the result back and synchronises.  Device scratch is cached inside
+ * the plan between calls (so this entry point is NOT re-entrant per plan).
+ * This is the call a ctypes/cgo/JNI binding over host arrays makes. */
+int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void* out_host,
+                          double* log_scale_host, int32_t* flags_host, int out_mode);
+
+const char* ctn_status_string(int status);
+const char* ctn_last_cuda_error(void);
+int ctn_abi_version(void);
+/* Number of visible CUDA devices with compute capability 10.x (0 = none). */
+int ctn_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTN_B200_H */
