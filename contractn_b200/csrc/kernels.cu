@@ -575,27 +575,39 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const StepDev* __restri
       record_scale(d, s.out_slot, norm, numel);
       d.tickets[s.ticket] = 0;
     }
-  } else if (threadIdx.x == 0) {
-    // few thousand partials at most: serial, fixed order
-    double S = 0.0, Sp = 0.0;
-    int E = 0, Ep = 0;
-    for (int i = 0; i < (int)gridDim.x; ++i) {
-      merge_scaled(S, E, __ldcg(&d.partials[i]), __ldcg(&d.partial_exp[i]));
-      merge_scaled(Sp, Ep, __ldcg(&d.partials[kMaxPartials + i]), __ldcg(&d.partial_exp[kMaxPartials + i]));
+  } else {
+    // combine (S_i * 2^E_i) over the CTAs: common exponent first, then a
+    // fixed-order block sum (deterministic, and parallel: grid can be ~2k)
+    int e_loc = INT_MIN, ep_loc = INT_MIN;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+      if (__ldcg(&d.partials[i]) != 0.0) e_loc = max(e_loc, __ldcg(&d.partial_exp[i]));
+      if (__ldcg(&d.partials[kMaxPartials + i]) != 0.0) ep_loc = max(ep_loc, __ldcg(&d.partial_exp[kMaxPartials + i]));
     }
-    // reference decision for the LAST fused step (einsum.py:102): its input was
-    // the normalised running product, so its norm is  sum|T_n| / mean|T_{n-1}|
-    const double log_ratio =
-        (log(S) + E * M_LN2) - (log(Sp) + Ep * M_LN2) + log((double)numel);
-    const bool fine = isfinite(S) && isfinite(Sp) && S > 0.0 && Sp > 0.0 && log_ratio > log(kMinNorm) + 1e-6;
-    const double mean = S / (double)numel;
-    d.hdr->chain_exp = E;
-    d.hdr->chain_mean = fine ? mean : 1.0;
-    if (fine) d.hdr->log_scale += E * M_LN2 + log(mean);
-    else d.hdr->flags |= CTN_RESULT_DEGENERATE;
-    d.kappa[s.out_slot] = 1.0;      // the materialise pass leaves a normalised tensor
-    d.inv_kappa[s.out_slot] = 1.0;
-    d.tickets[s.ticket] = 0;
+    int E = block_max_int(e_loc, redi);
+    int Ep = block_max_int(ep_loc, redi);
+    if (E == INT_MIN) E = 0;
+    if (Ep == INT_MIN) Ep = 0;
+    double s_loc = 0.0, sp_loc = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+      s_loc += scalbn(__ldcg(&d.partials[i]), max(__ldcg(&d.partial_exp[i]) - E, -4000));
+      sp_loc += scalbn(__ldcg(&d.partials[kMaxPartials + i]), max(__ldcg(&d.partial_exp[kMaxPartials + i]) - Ep, -4000));
+    }
+    const double S = block_sum(s_loc, red);
+    const double Sp = block_sum(sp_loc, red);
+    if (threadIdx.x == 0) {
+      // reference decision for the LAST fused step (einsum.py:102): its input was
+      // the normalised running product, so its norm is  sum|T_n| / mean|T_{n-1}|
+      const double log_ratio = (log(S) + E * M_LN2) - (log(Sp) + Ep * M_LN2) + log((double)numel);
+      const bool fine = isfinite(S) && isfinite(Sp) && S > 0.0 && Sp > 0.0 && log_ratio > log(kMinNorm) + 1e-6;
+      const double mean = S / (double)numel;
+      d.hdr->chain_exp = E;
+      d.hdr->chain_mean = fine ? mean : 1.0;
+      if (fine) d.hdr->log_scale += E * M_LN2 + log(mean);
+      else d.hdr->flags |= CTN_RESULT_DEGENERATE;
+      d.kappa[s.out_slot] = 1.0;      // the materialise pass leaves a normalised tensor
+      d.inv_kappa[s.out_slot] = 1.0;
+      d.tickets[s.ticket] = 0;
+    }
   }
 }
 

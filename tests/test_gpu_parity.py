@@ -145,9 +145,11 @@ def test_fused_chain_matches_stepwise_and_oracle(gpu_engine):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_fused_chain_extreme_ranges(gpu_engine, dtype):
-    """Products that under/overflow the dtype without the per-element exponent."""
+    """Products that under/overflow the dtype without the per-element exponent.
+    (Operands must keep sum|T_hat * v| above the reference's 1e-7 threshold,
+    einsum.py:102, or the reference itself stops rescaling and underflows.)"""
     rng = np.random.default_rng(7)
-    for lo, hi, n in [(1e-30, 2e-30, 64), (1e25, 3e25, 48), (1e-3, 1e3, 300)]:
+    for lo, hi, n in [(1e-9, 2e-9, 64), (1e25, 3e25, 48), (1e-3, 1e3, 300)]:
         ops = [rng.uniform(lo, hi, (3, 1000)).astype(dtype) for _ in range(n)]
         einstr = ",".join(["ab"] * n) + "->ab"
         lst = planner.contract_path(einstr, *[o.shape for o in ops])[1]
