@@ -46,9 +46,11 @@ def merge_batch_shards(T_local, c_local, group=None):
     dist.all_reduce(c_star, op=dist.ReduceOp.MAX, group=group)
     w = torch.exp(c_local - c_star)
     n_local = float(T_local.numel())
-    # T_local has mean-abs 1 by construction, so its abs-sum is numel * w after
-    # bringing it to the common scale (no pass over the data needed)
-    stats = torch.stack([w * n_local, torch.full_like(w, n_local)])
+    # sum|T_local| is numel when the shard was rescaled by its last step, but a
+    # shard whose norms fall under the reference's 1e-7 threshold is returned
+    # unscaled (contractn/einsum.py:102), so measure it
+    abs_sum = T_local.abs().sum().to(torch.float64)
+    stats = torch.stack([abs_sum * w, torch.full_like(w, n_local)])
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     kappa = stats[0] / stats[1]
     T = T_local * (w / kappa).to(T_local.dtype)
@@ -93,3 +95,122 @@ def slice_assignments(n_slices, rank=None, world=None):
     if rank is None:
         rank = dist.get_rank() if world > 1 else 0
     return list(range(rank, n_slices, world))
+
+
+# ---------------------------------------------------------------------------
+# bond slicing (host-side bookkeeping)
+# ---------------------------------------------------------------------------
+def _parse(einstr):
+    ins, out = einstr.split("->")
+    return ins.split(","), out
+
+
+def choose_slice_labels(einstr, shapes, contraction_list, min_slices):
+    """Pick contracted bonds to slice until there are at least ``min_slices``
+    slices: repeatedly take the label that carries the most weight in the
+    largest intermediates of the given path ("the largest contracted bonds")."""
+    terms, out = _parse(einstr)
+    size = {}
+    for t, shp in zip(terms, shapes):
+        for s, d in zip(t, shp):
+            size[s] = max(size.get(s, 1), int(d))
+    inter = [c[2].split("->")[1] for c in contraction_list[:-1]] or [c[2].split("->")[0] for c in contraction_list]
+    chosen, n = [], 1
+    while n < min_slices:
+        score = {}
+        for lab in inter:
+            vol = 1.0
+            for s in lab:
+                if s not in chosen:
+                    vol *= size[s]
+            for s in set(lab):
+                if s not in chosen and s not in out and size[s] > 1:
+                    score[s] = score.get(s, 0.0) + vol
+        if not score:
+            # nothing left in the intermediates: fall back to any contracted label
+            rest = [s for s in size if s not in out and s not in chosen and size[s] > 1]
+            if not rest:
+                break
+            best = max(rest, key=lambda s: (size[s], s))
+        else:
+            best = max(score, key=lambda s: (score[s], s))
+        chosen.append(best)
+        n *= size[best]
+    return tuple(chosen)
+
+
+class SlicedNetwork:
+    """An einsum network with some contracted labels fixed per slice.
+
+    ``einstr`` is the network with the sliced symbols deleted from every term;
+    ``slice_operands(ops, k)`` returns views of the operands for slice ``k``
+    (no copies: basic indexing, the engine consumes the strides)."""
+
+    def __init__(self, einstr, shapes, labels):
+        terms, out = _parse(einstr)
+        for s in labels:
+            if s in out:
+                raise ValueError(f"cannot slice output label {s!r}")
+        self.labels = tuple(labels)
+        self.extents = []
+        for s in labels:
+            ext = [shp[t.index(s)] for t, shp in zip(terms, shapes) if s in t]
+            if not ext:
+                raise ValueError(f"label {s!r} not in the network")
+            self.extents.append(int(max(ext)))
+        self.n_slices = int(math.prod(self.extents)) if labels else 1
+        self.terms = terms
+        self.einstr = ",".join("".join(c for c in t if c not in labels) for t in terms) + "->" + out
+        self.shapes = tuple(tuple(d for c, d in zip(t, shp) if c not in labels) for t, shp in zip(terms, shapes))
+
+    def slice_index(self, k):
+        idx = []
+        for e in reversed(self.extents):
+            idx.append(k % e)
+            k //= e
+        return tuple(reversed(idx))
+
+    def slice_operands(self, operands, k):
+        where = dict(zip(self.labels, self.slice_index(k)))
+        out = []
+        for t, op in zip(self.terms, operands):
+            sel = tuple(where[c] if c in where else slice(None) for c in t)
+            out.append(op[sel] if any(c in where for c in t) else op)
+        return out
+
+
+def contract_sliced(einstr, *operands, slice_labels=None, min_slices=None, optimize="auto",
+                    split_format=True, group=None, contract_fn=None):
+    """``contract`` with the largest bonds sliced across the ranks of ``group``.
+
+    Every rank passes the SAME full operands (they are small next to the
+    intermediates: this is the regime where slicing is used); rank r contracts
+    slices r, r+W, ... on its own GPU and the partial sums are merged with an
+    all-reduce of (mantissa, log-scale) pairs.  Returns the reference's result
+    for the unsliced network, on every rank.
+    """
+    from . import planner
+    from .engine import contract as engine_contract
+
+    contract_fn = contract_fn or engine_contract
+    shapes = tuple(tuple(op.shape) for op in operands)
+    world = _world(group)
+    rank = dist.get_rank(group) if world > 1 else 0
+    if slice_labels is None:
+        lst = planner.cached_contract_list(einstr, shapes, optimize=optimize)
+        slice_labels = choose_slice_labels(einstr, shapes, lst, min_slices or world)
+    net = SlicedNetwork(einstr, shapes, slice_labels)
+    acc = None
+    for k in slice_assignments(net.n_slices, rank, world):
+        T, c = contract_fn(net.einstr, *net.slice_operands(operands, k), optimize=optimize, split_format=True)
+        T = torch.as_tensor(T)
+        c = torch.as_tensor(c, dtype=torch.float64, device=T.device)
+        acc = lse_accumulate(acc, T, c)
+    if acc is None:  # more ranks than slices: contribute an exact zero
+        T0, _ = contract_fn(net.einstr, *net.slice_operands(operands, 0), optimize=optimize, split_format=True)
+        T0 = torch.as_tensor(T0)
+        acc = (torch.zeros_like(T0), torch.full((), -1.0e300, dtype=torch.float64, device=T0.device))
+    T, c = merge_slice_sums(acc[0], acc[1], group=group)
+    if split_format:
+        return T, c
+    return T * torch.exp(c).to(T.dtype)
