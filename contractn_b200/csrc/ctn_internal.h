@@ -24,6 +24,7 @@ enum LaunchKind : int32_t {
   kGemm = 3,
   kFinalize = 4,
   kMaterialize = 5,  // second pass of a tracked Hadamard chain
+  kGemmReduce = 6,   // second pass of a split-K GEMM
 };
 
 // One loop index of a step: extent and element stride in every input.
@@ -47,6 +48,10 @@ struct GemmDev {
   GemmMode n[kGemmMaxModes];
   GemmMode k[kGemmMaxModes];
   int64_t B, M, N, K;
+  int32_t cfg;          // tile configuration (gemm.cu)
+  int32_t splits;       // split-K factor (1 = single pass)
+  int32_t la, lb;       // shared-memory staging layout of A and B
+  int64_t scratch_off;  // split-K partial tiles, byte offset in the arena
 };
 
 // Device-side description of one step.
@@ -150,7 +155,10 @@ struct ExecCtx {
 cudaError_t launch_generic(const ExecCtx& c, const Launch& l);
 cudaError_t launch_chain(const ExecCtx& c, const Launch& l, bool vec_ok);
 cudaError_t launch_interp(const ExecCtx& c, const Launch& l);
-cudaError_t launch_gemm(const ExecCtx& c, const Launch& l);
+cudaError_t launch_gemm(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);
+cudaError_t launch_gemm_reduce(const ExecCtx& c, const Launch& l);
+void gemm_configure(const Plan& p, GemmDev& g);
+size_t gemm_scratch_bytes(const GemmDev& g);
 cudaError_t launch_finalize(const ExecCtx& c, const Launch& l);
 cudaError_t launch_materialize(const ExecCtx& c, const Launch& l, bool vec_ok);
 bool gemm_supported(const Plan& p, const StepDev& s, const GemmDev& g);

@@ -406,16 +406,25 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
       p.modes.insert(p.modes.end(), ls.k_modes.begin(), ls.k_modes.end());
       sd.kind = (ls.tiny && allow_interp) ? kInterp : kGeneric;
       if (sd.kind == kGeneric && allow_gemm && ls.has_gemm) {
-        sd.gemm_off = (int32_t)p.gemms.size();
-        p.gemms.push_back(ls.gemm);
-        if (gemm_supported(p, sd, ls.gemm)) sd.kind = kGemm;
-        else { p.gemms.pop_back(); sd.gemm_off = -1; }
+        if (gemm_supported(p, sd, ls.gemm)) {
+          sd.kind = kGemm;
+          sd.gemm_off = (int32_t)p.gemms.size();
+          gemm_configure(p, ls.gemm);
+          p.gemms.push_back(ls.gemm);
+        }
       }
     }
     // place the output, then release the inputs (never alias within a step)
     Slot& out = p.slots[ls.out_slot];
     if (!out.is_final) out.ws_offset = (int64_t)arena.alloc((size_t)out.numel * p.elem);
     size_t scratch_bytes = 0;
+    if (sd.kind == kGemm) {
+      scratch_bytes = gemm_scratch_bytes(p.gemms[sd.gemm_off]);
+      if (scratch_bytes) {
+        sd.scratch_off = (int64_t)arena.alloc(scratch_bytes);
+        p.gemms[sd.gemm_off].scratch_off = sd.scratch_off;
+      }
+    }
     if (sd.kind == kChain && sd.tracked) {
       // one exponent per tile of the chain output (tile = 1024 f64 / 2048 f32 at most;
       // sized for the smallest tile the kernel variants use)
@@ -437,6 +446,8 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
       p.launches.push_back(Launch{sd.kind, idx, idx, bytes, ls.flops});
       if (sd.kind == kChain && sd.tracked)
         p.launches.push_back(Launch{kMaterialize, idx, idx, 2 * out.numel * (int64_t)p.elem, 0.0});
+      if (sd.kind == kGemm && p.gemms[sd.gemm_off].splits > 1)
+        p.launches.push_back(Launch{kGemmReduce, idx, idx, (int64_t)scratch_bytes, 0.0});
     }
   }
   // the last launch must leave the canonical (T/mean|T|, log-scale) pair:
@@ -454,7 +465,7 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
   return CTN_OK;
 }
 
-static int upload_plan(Plan& p) {
+static int query_device(Plan& p) {
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0) {
@@ -464,9 +475,14 @@ static int upload_plan(Plan& p) {
     return CTN_OK;
   }
   CTN_CUDA(cudaGetDevice(&p.device));
-  cudaDeviceProp prop;
-  CTN_CUDA(cudaGetDeviceProperties(&prop, p.device));
-  p.sm_count = prop.multiProcessorCount;
+  int sms = 0;
+  CTN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device));
+  p.sm_count = sms;
+  return CTN_OK;
+}
+
+static int upload_plan(Plan& p) {
+  if (p.device < 0) return CTN_OK;
   auto up = [](void** dst, const void* src, size_t bytes) -> cudaError_t {
     if (bytes == 0) { *dst = nullptr; return cudaSuccess; }
     cudaError_t e = cudaMalloc(dst, bytes);
@@ -527,7 +543,8 @@ int ctn_plan_create(const ctn_plan_desc* desc, ctn_plan** plan_out) {
   if (!h) return CTN_ERR_NOMEM;
   int rc;
   try {
-    rc = build_plan(*desc, h->p);
+    rc = query_device(h->p);
+    if (rc == CTN_OK) rc = build_plan(*desc, h->p);
     if (rc == CTN_OK) rc = upload_plan(h->p);
   } catch (const std::bad_alloc&) {
     rc = CTN_ERR_NOMEM;
@@ -592,7 +609,7 @@ double ctn_plan_step_bytes(const ctn_plan* plan) {
   if (!plan) return 0.0;
   double b = 0;
   for (auto& l : plan->p.launches)
-    if (l.kind != kFinalize && l.kind != kMaterialize) b += (double)l.bytes;
+    if (l.kind != kFinalize && l.kind != kMaterialize && l.kind != kGemmReduce) b += (double)l.bytes;
   return b;
 }
 
@@ -647,7 +664,12 @@ static int execute_impl(const ctn_plan* plan, const void* const* operands, void*
       case kChain: e = launch_chain(ctx, l, chain_vec_ok(p.steps[l.first_step])); break;
       case kMaterialize: e = launch_materialize(ctx, l, chain_vec_ok(p.steps[l.first_step])); break;
       case kInterp: e = launch_interp(ctx, l); break;
-      case kGemm: e = launch_gemm(ctx, l); break;
+      case kGemm: {
+        const StepDev& gs = p.steps[l.first_step];
+        e = launch_gemm(ctx, l, ((uintptr_t)ptrs[gs.in_slot[0]] & 15) == 0, ((uintptr_t)ptrs[gs.in_slot[1]] & 15) == 0);
+        break;
+      }
+      case kGemmReduce: e = launch_gemm_reduce(ctx, l); break;
       case kFinalize: e = launch_finalize(ctx, l); break;
       default: return CTN_ERR_INVALID;
     }

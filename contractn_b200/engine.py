@@ -34,7 +34,7 @@ CTN_PLAN_EXACT_STEPS = 1
 CTN_PLAN_NO_INTERPRETER = 2
 CTN_PLAN_NO_GEMM = 4
 CTN_RESULT_DEGENERATE = 1
-LAUNCH_KINDS = ("generic", "chain", "interp", "gemm", "finalize", "materialize")
+LAUNCH_KINDS = ("generic", "chain", "interp", "gemm", "finalize", "materialize", "gemm_reduce")
 
 EXPORTS = (
     "ctn_plan_create", "ctn_plan_destroy", "ctn_plan_workspace_bytes",

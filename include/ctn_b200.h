@@ -127,7 +127,7 @@ int ctn_plan_num_launches(const ctn_plan* plan);      /* kernels per execute    
 double ctn_plan_flops(const ctn_plan* plan);          /* path FLOPs, opt_einsum convention */
 double ctn_plan_step_bytes(const ctn_plan* plan);     /* sum over launches of operand+result bytes */
 /* kind of launch i: 0 generic, 1 hadamard-chain, 2 interpreter, 3 gemm, 4 finalize,
- * 5 chain materialise pass; -1 past the end */
+ * 5 chain materialise pass, 6 split-K reduce pass; -1 past the end */
 int ctn_plan_launch_kind(const ctn_plan* plan, int i);
 
 /* Run the plan: the body of _core_contract (contractn/einsum.py:341-393) plus

@@ -1,0 +1,120 @@
+"""The strided DMMA GEMM kernel against numpy on shapes that exercise every
+staging layout (K-fast / MN-fast / element-wise), tile configuration, batch,
+multi-mode groups, ragged edges and split-K.  float64, rtol 1e-12."""
+import numpy as np
+import pytest
+
+from oracle import contract_oracle as oracle
+from contractn_b200 import planner
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # (einsum, shapes, what)
+    ("ab,bc->ac", [(256, 128), (128, 192)], "plain NN: A K-fast, B N-fast"),
+    ("ab,cb->ac", [(200, 64), (150, 64)], "NT: both K-fast"),
+    ("ba,bc->ac", [(64, 200), (64, 150)], "TN: both MN-fast"),
+    ("ba,cb->ac", [(96, 130), (70, 96)], "TT"),
+    ("ab,bc->ca", [(130, 40), (40, 70)], "transposed output"),
+    ("ab,bc->ac", [(129, 67), (67, 131)], "odd sizes: element-wise staging, ragged tiles"),
+    ("ab,bc->ac", [(1000, 24), (24, 16)], "narrow N: 128x32 tiles"),
+    ("ab,bc->ac", [(16, 24), (24, 1000)], "narrow M: 32x128 tiles"),
+    ("ab,b->a", [(512, 300), (300,)], "GEMV"),
+    ("a,ab->b", [(300,), (300, 512)], "vector-matrix"),
+    ("ab,ab->", [(300, 400), (300, 400)], "DOT: split-K"),
+    ("ab,ba->", [(300, 400), (400, 300)], "transposed DOT"),
+    ("abc,bcd->ad", [(40, 30, 20), (30, 20, 50)], "two contiguous summed modes fuse"),
+    ("abc,cbd->ad", [(40, 30, 20), (20, 30, 50)], "two summed modes, not fusable in B"),
+    ("bij,bjk->bik", [(6, 50, 70), (6, 70, 40)], "batched"),
+    ("ibj,jbk->bik", [(50, 6, 70), (70, 6, 40)], "batch index in the middle"),
+    ("br,prs->bps", [(300, 64), (2, 64, 64)], "cfg 3 step (TDOT)"),
+    ("dbc,eb->dce", [(20, 64, 30), (50, 64)], "cfg 4 Tucker step (TDOT, summed mode mid-tensor)"),
+    ("cab,da->bcd", [(30, 64, 40), (50, 64)], "cfg 4 CP step"),
+    ("abcdefgh,efxy->abcdghxy", [(4,) * 8, (4, 4, 8, 8)], "cfg 5 boundary step: summed legs mid-tensor"),
+    ("abcd,cdef->abef", [(8, 8, 8, 8), (8, 8, 8, 8)], "PEPS block"),
+    ("ab,bc->ac", [(40, 5000), (5000, 30)], "small output, long K: split-K"),
+    ("aab,bc->ac", [(20, 20, 64), (64, 30)], "diagonal of an operand"),
+    ("ab,bc->ac", [(64, 1), (300, 50)], "broadcast summed index -> not a GEMM, generic"),
+]
+
+
+@pytest.mark.parametrize("einstr,shapes,what", CASES, ids=[c[2] for c in CASES])
+def test_gemm_step(gpu_engine, einstr, shapes, what):
+    rng = np.random.default_rng(hash(einstr) % (2 ** 32))
+    ops = [rng.uniform(0.1, 1.0, s) for s in shapes]
+    lst = planner.contract_path(einstr, *shapes)[1]
+    T, c = gpu_engine.core_contract(ops, lst)
+    want_T, want_c = oracle.core_contract(ops, lst)
+    np.testing.assert_allclose(T, want_T, rtol=1e-12, err_msg=what)
+    assert abs(float(c) - float(want_c)) < 1e-9
+
+
+def test_gemm_kinds_are_selected(gpu_engine):
+    def kinds(einstr, shapes):
+        lst = planner.contract_path(einstr, *shapes)[1]
+        return gpu_engine.Plan(lst, shapes, np.float64).launch_kinds
+
+    assert kinds("ab,bc->ac", [(256, 128), (128, 192)]) == ("gemm", "finalize")
+    assert kinds("ab,ab->", [(300, 400)] * 2) == ("gemm", "gemm_reduce", "finalize")
+    assert kinds("bps,bp->bs", [(300, 2, 64), (300, 2)]) == ("generic", "finalize")
+
+
+def test_gemm_on_strided_views_and_misaligned_pointers(gpu_engine):
+    rng = np.random.default_rng(4)
+    big_a = rng.uniform(0.1, 1, (300, 260))
+    big_b = rng.uniform(0.1, 1, (270, 310))
+    a = big_a[3:259:2, 1:201]       # row stride 520, odd element offset -> 8-byte staging
+    b = big_b[5:205, 7:247:3]       # column stride 3
+    lst = planner.contract_path("ab,bc->ac", a.shape, b.shape)[1]
+    T, c = gpu_engine.core_contract([a, b], lst)
+    want_T, want_c = oracle.core_contract([a, b], lst)
+    np.testing.assert_allclose(T, want_T, rtol=1e-12)
+    assert abs(float(c) - float(want_c)) < 1e-9
+    import torch
+
+    ta = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    flat = torch.empty(ta.numel() + 1, dtype=torch.float64, device="cuda")
+    mis = flat[1:].view(ta.shape)  # 8-byte but not 16-byte aligned base
+    mis.copy_(ta)
+    tb = torch.as_tensor(np.ascontiguousarray(b)).cuda()
+    T2, c2 = gpu_engine.core_contract([mis, tb], lst)
+    np.testing.assert_allclose(T2.cpu().numpy(), want_T, rtol=1e-12)
+
+
+def test_gemm_signed_data_normwise(gpu_engine):
+    rng = np.random.default_rng(8)
+    a, b = rng.normal(size=(300, 700)), rng.normal(size=(700, 200))
+    lst = planner.contract_path("ab,bc->ac", a.shape, b.shape)[1]
+    T, c = gpu_engine.core_contract([a, b], lst)
+    want_T, want_c = oracle.core_contract([a, b], lst)
+    assert np.linalg.norm(T - want_T) <= 1e-12 * np.linalg.norm(want_T)
+    assert abs(float(c) - float(want_c)) < 1e-9
+
+
+def test_peps_6x6_d4_against_oracle(gpu_engine):
+    """cfg 5 in small: closed 6x6 grid, D = 4, greedy path (GEMM + TDOT steps)."""
+    rng = np.random.default_rng(1005)
+    L, D = 6, 4
+    sym, terms, shapes = {}, [], []
+
+    def s(key):
+        if key not in sym:
+            sym[key] = planner.get_symbol(len(sym))
+        return sym[key]
+
+    for r in range(L):
+        for c in range(L):
+            t = ""
+            if r > 0: t += s(("v", r - 1, c))
+            if c > 0: t += s(("h", r, c - 1))
+            if r < L - 1: t += s(("v", r, c))
+            if c < L - 1: t += s(("h", r, c))
+            terms.append(t)
+            shapes.append((D,) * len(t))
+    einstr = ",".join(terms) + "->"
+    ops = [rng.uniform(0, 1, sh) for sh in shapes]
+    lst = planner.contract_path(einstr, *shapes, optimize="greedy")[1]
+    T, c = gpu_engine.core_contract(ops, lst)
+    want_T, want_c = oracle.core_contract(ops, lst)
+    np.testing.assert_allclose(T, want_T, rtol=1e-12)
+    assert abs(float(c) - float(want_c)) < 1e-9
