@@ -158,6 +158,9 @@ cudaError_t launch_interp(const ExecCtx& c, const Launch& l);
 cudaError_t launch_gemm(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);
 cudaError_t launch_gemm_reduce(const ExecCtx& c, const Launch& l);
 void gemm_configure(const Plan& p, GemmDev& g);
+bool gemm_tf32_supported(const Plan& p, const StepDev& s, const GemmDev& g);
+void gemm_tf32_configure(const Plan& p, GemmDev& g);
+cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);
 size_t gemm_scratch_bytes(const GemmDev& g);
 cudaError_t launch_finalize(const ExecCtx& c, const Launch& l);
 cudaError_t launch_materialize(const ExecCtx& c, const Launch& l, bool vec_ok);

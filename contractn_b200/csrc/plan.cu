@@ -411,6 +411,11 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
           sd.gemm_off = (int32_t)p.gemms.size();
           gemm_configure(p, ls.gemm);
           p.gemms.push_back(ls.gemm);
+        } else if (gemm_tf32_supported(p, sd, ls.gemm)) {
+          sd.kind = kGemm;
+          sd.gemm_off = (int32_t)p.gemms.size();
+          gemm_tf32_configure(p, ls.gemm);
+          p.gemms.push_back(ls.gemm);
         }
       }
     }
@@ -666,7 +671,8 @@ static int execute_impl(const ctn_plan* plan, const void* const* operands, void*
       case kInterp: e = launch_interp(ctx, l); break;
       case kGemm: {
         const StepDev& gs = p.steps[l.first_step];
-        e = launch_gemm(ctx, l, ((uintptr_t)ptrs[gs.in_slot[0]] & 15) == 0, ((uintptr_t)ptrs[gs.in_slot[1]] & 15) == 0);
+        const bool a_al = ((uintptr_t)ptrs[gs.in_slot[0]] & 15) == 0, b_al = ((uintptr_t)ptrs[gs.in_slot[1]] & 15) == 0;
+        e = p.dtype == CTN_F32 ? launch_gemm_tf32(ctx, l, a_al, b_al) : launch_gemm(ctx, l, a_al, b_al);
         break;
       }
       case kGemmReduce: e = launch_gemm_reduce(ctx, l); break;

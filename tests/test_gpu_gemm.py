@@ -118,3 +118,49 @@ def test_peps_6x6_d4_against_oracle(gpu_engine):
     want_T, want_c = oracle.core_contract(ops, lst)
     np.testing.assert_allclose(T, want_T, rtol=1e-12)
     assert abs(float(c) - float(want_c)) < 1e-9
+
+
+# ---------------------------------------------------------------------------
+# float32: tcgen05 3xTF32 kernel (M, N >= 16) and generic kernel otherwise
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("einstr,shapes,what", CASES, ids=[c[2] for c in CASES])
+def test_gemm_step_f32(gpu_engine, einstr, shapes, what):
+    """north_star tolerance for float32 values: rtol 1e-5 (against float64 truth)."""
+    rng = np.random.default_rng(hash(einstr) % (2 ** 32))
+    ops = [rng.uniform(0.1, 1.0, s).astype(np.float32) for s in shapes]
+    lst = planner.contract_path(einstr, *shapes)[1]
+    T, c = gpu_engine.core_contract(ops, lst)
+    assert T.dtype == np.float32
+    ops64 = [o.astype(np.float64) for o in ops]
+    want_T, want_c = oracle.core_contract(ops64, lst)
+    np.testing.assert_allclose(T.astype(np.float64), want_T, rtol=1e-5, err_msg=what)
+    assert abs(float(c) - float(want_c)) < 1e-5
+
+
+def test_tf32_kernel_is_selected_and_accurate_for_long_k(gpu_engine):
+    """Accumulation-chain control: K = 8192 still meets rtol 1e-5 on positive data."""
+    rng = np.random.default_rng(12)
+    a = rng.uniform(0.0, 1.0, (256, 8192)).astype(np.float32)
+    b = rng.uniform(0.0, 1.0, (8192, 192)).astype(np.float32)
+    lst = planner.contract_path("ab,bc->ac", a.shape, b.shape)[1]
+    plan = gpu_engine.Plan(lst, [a.shape, b.shape], np.float32)
+    assert plan.launch_kinds == ("gemm", "finalize")
+    T, c, _ = plan.execute_host([a, b])
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    got = T.astype(np.float64) * np.exp(c)
+    assert np.abs(got / want - 1).max() < 3e-5
+    # the normalised mantissa (what split format returns) is tighter: the
+    # accumulator's truncation bias is common to all entries and cancels
+    wT, wc = oracle.canonical_split(want)
+    np.testing.assert_allclose(T.astype(np.float64), wT, rtol=1e-5)
+
+
+def test_tf32_signed_data_normwise(gpu_engine):
+    rng = np.random.default_rng(13)
+    a = rng.normal(size=(300, 700)).astype(np.float32)
+    b = rng.normal(size=(700, 200)).astype(np.float32)
+    lst = planner.contract_path("ab,bc->ac", a.shape, b.shape)[1]
+    T, c = gpu_engine.core_contract([a, b], lst)
+    want = a.astype(np.float64) @ b.astype(np.float64)
+    got = T.astype(np.float64) * np.exp(float(c))
+    assert np.linalg.norm(got - want) <= 1e-5 * np.linalg.norm(want)
