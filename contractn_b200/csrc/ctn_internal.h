@@ -13,7 +13,8 @@ namespace ctn {
 
 constexpr int kMaxIn = 8;          // inputs of one generic step
 constexpr int kChainMaxIn = 512;   // inputs of one fused Hadamard-chain launch
-constexpr int kMaxPartials = 148 * 16;  // upper bound on the grid of any reducing kernel
+constexpr int kMaxPartials = 148 * 16;
+constexpr int kInterpMaxSteps = 4096;   // steps per interpreter launch (ready flags live in shared memory)  // upper bound on the grid of any reducing kernel
 constexpr double kMinNorm = 1e-7;  // contractn/einsum.py:94
 
 // launch kinds (ctn_plan_launch_kind)
@@ -68,6 +69,7 @@ struct StepDev {
   int32_t ticket;      // index of this step's arrival counter
   int32_t is_final;    // output of the whole plan
   int32_t tracked;     // chain: per-element exponent tracking (n_in > 2)
+  int32_t dep[kMaxIn]; // interp: launch-local index of the step producing input i (-1: ready at launch)
   int64_t scratch_off; // chain: byte offset of the per-tile exponent array in the arena
   int64_t out_numel;
   int64_t k_numel;

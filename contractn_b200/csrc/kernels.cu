@@ -138,13 +138,158 @@ __global__ void __launch_bounds__(kThreads) generic_step_kernel(const StepDev* _
   }
 }
 
+// Row-wise variant for steps whose innermost output mode is long: a CTA takes
+// one value of all outer output modes (decomposed once per row, not per element)
+// and its threads run along the innermost mode, so loads and stores are
+// coalesced whenever that mode is contiguous and no div/mod is left in the loop.
+constexpr int kRowsKTable = 512;  // summed-mode offsets kept in shared memory up to this many
+
+template <typename T, int NIN, typename ACC>
+__global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* __restrict__ steps,
+                                                                const ModeDev* __restrict__ all_modes, int step_idx,
+                                                                DevState d) {
+  __shared__ double red[33];
+  __shared__ bool last_block;
+  __shared__ int64_t row_base[NIN];
+  __shared__ int64_t k_off[NIN][kRowsKTable];
+  const StepDev& s = steps[step_idx];
+  const ModeDev* modes = all_modes + s.mode_off;
+  const T* in[NIN];
+  double alpha = 1.0;
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) {
+    in[i] = (const T*)d.ptrs[s.in_slot[i]];
+    alpha *= d.inv_kappa[s.in_slot[i]];
+  }
+  T* out = (T*)d.ptrs[s.out_slot];
+  const ModeDev& inner = modes[s.n_out_modes - 1];
+  const int64_t inner_n = inner.extent;
+  const int64_t n_rows = s.out_numel / inner_n;
+  const int64_t chunks = (inner_n + kThreads - 1) / kThreads;
+  const int64_t work = n_rows * chunks;
+  const int kn = (int)s.k_numel;  // <= kRowsKTable (checked by the launcher)
+  const int n_k_modes = s.n_k_modes, n_outer = s.n_out_modes - 1;
+  const ModeDev* km = modes + s.n_out_modes;
+  // offsets of every summed index, once per CTA
+  for (int k = threadIdx.x; k < kn; k += blockDim.x) {
+    int64_t o[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) o[i] = 0;
+    int r = k;
+    for (int m = n_k_modes - 1; m >= 0; --m) {
+      const int e = (int)km[m].extent;
+      const int idx = r % e;
+      r /= e;
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) o[i] += (int64_t)idx * km[m].stride[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) k_off[i][k] = o[i];
+  }
+  int64_t inner_stride[NIN];
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) inner_stride[i] = inner.stride[i];
+  const ACC alpha_t = (ACC)alpha;
+
+  double local = 0.0;
+  for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
+    const int64_t row = w / chunks, chunk = w - row * chunks;
+    __syncthreads();
+    if (threadIdx.x < NIN) {
+      int64_t o = 0, rem = row;
+      for (int m = n_outer - 1; m >= 0; --m) {
+        const int64_t e = modes[m].extent;
+        const int64_t idx = rem % e;
+        rem /= e;
+        o += idx * modes[m].stride[threadIdx.x];
+      }
+      row_base[threadIdx.x] = o;
+    }
+    __syncthreads();
+    const int64_t j = chunk * kThreads + threadIdx.x;
+    if (j < inner_n) {
+      const T* p[NIN];
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) p[i] = in[i] + row_base[i] + j * inner_stride[i];
+      ACC acc;
+      if (n_k_modes == 0) {
+        acc = (ACC)1;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) acc *= (ACC)__ldg(p[i]);
+      } else {
+        acc = (ACC)0;
+        for (int k = 0; k < kn; ++k) {
+          ACC pr = (ACC)__ldg(p[0] + k_off[0][k]);
+#pragma unroll
+          for (int i = 1; i < NIN; ++i) pr *= (ACC)__ldg(p[i] + k_off[i][k]);
+          acc += pr;
+        }
+      }
+      const T r = (T)(acc * alpha_t);
+      out[row * inner_n + j] = r;
+      local += (double)fabs(r);
+    }
+  }
+  const double bsum = block_sum(local, red);
+  if (threadIdx.x == 0) {
+    d.partials[blockIdx.x] = bsum;
+    __threadfence();
+    const uint32_t t = atomicAdd(&d.tickets[s.ticket], 1u);
+    last_block = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_block) {
+    __threadfence();
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) acc += __ldcg(&d.partials[i]);
+    const double norm = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      record_scale(d, s.out_slot, norm, s.out_numel);
+      d.tickets[s.ticket] = 0;
+    }
+  }
+}
+
+template <typename T, typename ACC>
+static cudaError_t launch_rows(const ExecCtx& c, const Launch& l, int grid, int n_in) {
+  const Plan& p = *c.plan;
+  DevState d = dev_state(c);
+#define CTN_ROWS_CASE(N_)                                                                                         \
+  case N_:                                                                                                        \
+    generic_rows_kernel<T, N_, ACC><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d); \
+    break;
+  switch (n_in) {
+    CTN_ROWS_CASE(1)
+    CTN_ROWS_CASE(2)
+    CTN_ROWS_CASE(3)
+    CTN_ROWS_CASE(4)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef CTN_ROWS_CASE
+  return cudaGetLastError();
+}
+
 cudaError_t launch_generic(const ExecCtx& c, const Launch& l) {
   const Plan& p = *c.plan;
   const StepDev& s = p.steps[l.first_step];
-  int64_t blocks = (s.out_numel + kThreads - 1) / kThreads;
-  int64_t cap = std::min<int64_t>((int64_t)p.sm_count * 8, kMaxPartials);
-  int grid = (int)std::max<int64_t>(1, std::min(blocks, cap));
   DevState d = dev_state(c);
+  const int64_t cap = std::min<int64_t>((int64_t)p.sm_count * 8, kMaxPartials);
+  // long innermost output mode and few summed indices: row-wise kernel
+  if (s.n_out_modes >= 1 && s.k_numel <= kRowsKTable && s.n_in <= 4) {
+    const int64_t inner_n = p.modes[s.mode_off + s.n_out_modes - 1].extent;
+    if (inner_n >= 64) {
+      const int64_t work = (s.out_numel / inner_n) * ((inner_n + kThreads - 1) / kThreads);
+      const int grid = (int)std::max<int64_t>(1, std::min(work, cap));
+      // float data: short sums stay in fp32 (what the reference's einsum does too);
+      // long ones are accumulated in fp64
+      if (p.dtype == CTN_F64) return launch_rows<double, double>(c, l, grid, s.n_in);
+      if (s.k_numel <= 64) return launch_rows<float, float>(c, l, grid, s.n_in);
+      return launch_rows<float, double>(c, l, grid, s.n_in);
+    }
+  }
+  int64_t blocks = (s.out_numel + kThreads - 1) / kThreads;
+  int grid = (int)std::max<int64_t>(1, std::min(blocks, cap));
   if (p.dtype == CTN_F32)
     generic_step_kernel<float><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d);
   else
@@ -194,41 +339,72 @@ cudaError_t launch_finalize(const ExecCtx& c, const Launch& l) {
 }
 
 // ---------------------------------------------------------------------------
-// interpreter: a run of tiny steps in one CTA
+// interpreter: a run of tiny steps in ONE launch.  One CTA; every step is
+// executed by one warp (steps are dealt round-robin to the warps), warps only
+// wait for the steps that produce their inputs (ready flags in shared memory),
+// so independent branches of the contraction tree overlap and a dependent chain
+// costs one L2 round trip per step instead of a kernel launch.
 // ---------------------------------------------------------------------------
+constexpr int kInterpWarps = 8;
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads) interp_kernel(const StepDev* __restrict__ steps,
-                                                          const ModeDev* __restrict__ all_modes, int first, int last,
-                                                          DevState d, int dense, double* log_scale_out,
-                                                          int32_t* flags_out) {
-  __shared__ double red[33];
-  for (int si = first; si <= last; ++si) {
-    const StepDev& s = steps[si];
+__global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev* __restrict__ steps,
+                                                                  const ModeDev* __restrict__ all_modes, int first,
+                                                                  int last, DevState d, int dense,
+                                                                  double* log_scale_out, int32_t* flags_out) {
+  __shared__ volatile int ready[kInterpMaxSteps];
+  __shared__ double warp_log[kInterpWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_steps = last - first + 1;
+  for (int i = threadIdx.x; i < n_steps; i += blockDim.x) ready[i] = 0;
+  __syncthreads();
+  double log_acc = 0.0;  // lane 0 of each warp: sum of ln(kappa) of the steps it ran
+  for (int li = warp; li < n_steps; li += kInterpWarps) {
+    const StepDev& s = steps[first + li];
     const ModeDev* modes = all_modes + s.mode_off;
     const T* in[kMaxIn];
+#pragma unroll
+    for (int i = 0; i < kMaxIn; ++i) in[i] = i < s.n_in ? (const T*)d.ptrs[s.in_slot[i]] : nullptr;
+    T* out = (T*)d.ptrs[s.out_slot];
+    // wait for the producers of the inputs
+#pragma unroll
+    for (int i = 0; i < kMaxIn; ++i)
+      if (i < s.n_in && s.dep[i] >= 0)
+        while (ready[s.dep[i]] == 0) {}
+    __threadfence_block();
     double alpha = 1.0;
 #pragma unroll
-    for (int i = 0; i < kMaxIn; ++i) {
-      in[i] = nullptr;
-      if (i < s.n_in) {
-        in[i] = (const T*)d.ptrs[s.in_slot[i]];
-        alpha *= __ldcg(&d.inv_kappa[s.in_slot[i]]);
-      }
-    }
-    T* out = (T*)d.ptrs[s.out_slot];
+    for (int i = 0; i < kMaxIn; ++i)
+      if (i < s.n_in) alpha *= __ldcg(&d.inv_kappa[s.in_slot[i]]);
     const int numel = (int)s.out_numel;
     double local = 0.0;
-    for (int o = threadIdx.x; o < numel; o += blockDim.x) {
+    for (int o = lane; o < numel; o += 32) {
       const double v = step_element<T, true, uint32_t>(s, modes, in, (uint32_t)o);
       const T r = (T)(v * alpha);
       out[o] = r;
       local += fabs((double)r);
     }
-    const double norm = block_sum(local, red);
-    if (threadIdx.x == 0) record_scale(d, s.out_slot, norm, s.out_numel);
+    const double norm = warp_sum(local);
+    if (lane == 0) {
+      // stabilize (einsum.py:89-107); the log-scale is summed per warp, merged at the end
+      const bool rescale = norm > kMinNorm;
+      const double kappa = norm / (double)s.out_numel;
+      d.kappa[s.out_slot] = rescale ? kappa : 1.0;
+      d.inv_kappa[s.out_slot] = rescale ? 1.0 / kappa : 1.0;
+      if (rescale) log_acc += log(kappa);
+    }
     __threadfence_block();
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) ready[li] = 1;
   }
+  if (lane == 0) warp_log[warp] = log_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int w = 0; w < kInterpWarps; ++w) total += warp_log[w];  // fixed order
+    d.hdr->log_scale += total;
+  }
+  __syncthreads();
   const StepDev& s = steps[last];
   if (s.is_final) {
     T* out = (T*)d.ptrs[s.out_slot];
@@ -248,11 +424,13 @@ cudaError_t launch_interp(const ExecCtx& c, const Launch& l) {
   const Plan& p = *c.plan;
   DevState d = dev_state(c);
   if (p.dtype == CTN_F32)
-    interp_kernel<float><<<1, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
-                                                      c.out_mode == CTN_OUT_DENSE, c.log_scale_out, c.flags_out);
+    interp_kernel<float><<<1, kInterpWarps * 32, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
+                                                               c.out_mode == CTN_OUT_DENSE, c.log_scale_out,
+                                                               c.flags_out);
   else
-    interp_kernel<double><<<1, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
-                                                       c.out_mode == CTN_OUT_DENSE, c.log_scale_out, c.flags_out);
+    interp_kernel<double><<<1, kInterpWarps * 32, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
+                                                                c.out_mode == CTN_OUT_DENSE, c.log_scale_out,
+                                                                c.flags_out);
   return cudaGetLastError();
 }
 

@@ -376,6 +376,8 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
 
   // emit device steps + launches, placing intermediates in the arena
   Arena arena;
+  std::map<int32_t, int32_t> producer;  // slot -> index of the step that writes it
+  std::vector<std::pair<size_t, size_t>> deferred;  // buffers read inside the current interpreter launch
   const bool allow_interp = !(d.flags & CTN_PLAN_NO_INTERPRETER);
   const bool allow_gemm = !(d.flags & CTN_PLAN_NO_GEMM);
   for (size_t t = 0; t < lowered.size(); ++t) {
@@ -436,14 +438,38 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
       scratch_bytes = (size_t)((out.numel + 511) / 512 + 1) * sizeof(int32_t);
       sd.scratch_off = (int64_t)arena.alloc(scratch_bytes);
     }
+    // The interpreter runs independent steps of one launch concurrently, so a
+    // buffer read inside an interpreter launch must not be handed to a later
+    // step of the same launch: hold those releases back until the launch ends.
+    if (sd.kind != kInterp) {
+      for (auto& r : deferred) arena.release(r.first, r.second);
+      deferred.clear();
+    }
     for (auto s : ls.in_slots) {
       Slot& in = p.slots[s];
-      if (in.operand < 0 && in.ws_offset >= 0) arena.release((size_t)in.ws_offset, (size_t)in.numel * p.elem);
+      if (in.operand < 0 && in.ws_offset >= 0) {
+        if (sd.kind == kInterp) deferred.emplace_back((size_t)in.ws_offset, (size_t)in.numel * p.elem);
+        else arena.release((size_t)in.ws_offset, (size_t)in.numel * p.elem);
+      }
     }
     if (scratch_bytes) arena.release((size_t)sd.scratch_off, scratch_bytes);
     int32_t idx = (int32_t)p.steps.size();
+    const bool join = sd.kind == kInterp && !p.launches.empty() && p.launches.back().kind == kInterp &&
+                      idx - p.launches.back().first_step < kInterpMaxSteps;
+    if (sd.kind == kInterp) {
+      // dependencies inside the launch: the interpreter runs independent steps on different warps
+      const int32_t first = join ? p.launches.back().first_step : idx;
+      for (int i = 0; i < kMaxIn; ++i) {
+        sd.dep[i] = -1;
+        if (i < sd.n_in) {
+          auto it = producer.find(sd.in_slot[i]);
+          if (it != producer.end() && it->second >= first) sd.dep[i] = it->second - first;
+        }
+      }
+    }
+    producer[sd.out_slot] = idx;
     p.steps.push_back(sd);
-    if (sd.kind == kInterp && !p.launches.empty() && p.launches.back().kind == kInterp) {
+    if (join) {
       p.launches.back().last_step = idx;
       p.launches.back().bytes += bytes;
       p.launches.back().flops += ls.flops;
