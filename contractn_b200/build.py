@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libctn_b200.so")
-SOURCES = ["plan.cu", "kernels.cu", "gemm.cu", "gemm_tf32.cu"]
+SOURCES = ["plan.cu", "kernels.cu", "gemm.cu", "gemm_tf32.cu", "skinny.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -160,6 +160,8 @@ cudaError_t launch_interp(const ExecCtx& c, const Launch& l);
 cudaError_t launch_gemm(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);
 cudaError_t launch_gemm_reduce(const ExecCtx& c, const Launch& l);
 void gemm_configure(const Plan& p, GemmDev& g);
+int skinny_config(const Plan& p, const StepDev& s, const GemmDev& g);
+cudaError_t launch_skinny(const ExecCtx& c, const Launch& l);
 bool gemm_tf32_supported(const Plan& p, const StepDev& s, const GemmDev& g);
 void gemm_tf32_configure(const Plan& p, GemmDev& g);
 cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);

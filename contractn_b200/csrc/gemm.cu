@@ -38,6 +38,8 @@ struct TileCfg {
   static constexpr size_t SMEM = (size_t)kStages * STAGE_ELEMS * sizeof(double) + (size_t)2 * (BM + BN) * sizeof(int64_t);
 };
 using Cfg128x128 = TileCfg<2, 4, 8, 4>;
+using Cfg128x64 = TileCfg<4, 2, 4, 4>;   // 90 KB of shared memory, <= 128 registers: two CTAs per SM
+using Cfg64x128 = TileCfg<2, 4, 4, 4>;
 using Cfg128x32 = TileCfg<8, 1, 2, 4>;
 using Cfg32x128 = TileCfg<1, 8, 4, 2>;
 
@@ -144,7 +146,7 @@ __device__ __forceinline__ double frag(const double* tile, int row, int k) {
 }
 
 template <class Cfg, int LA, int LB>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, (Cfg::BM * Cfg::BN <= 128 * 64) ? 2 : 1)
     gemm_f64_kernel(const StepDev* __restrict__ steps, const GemmDev* __restrict__ gemms, int step_idx, DevState d) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, TM = Cfg::kTM, TN = Cfg::kTN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -390,8 +392,9 @@ bool gemm_supported(const Plan& p, const StepDev& s, const GemmDev& g) {
 }
 
 void gemm_configure(const Plan& p, GemmDev& g) {
-  g.cfg = (g.N <= 32) ? 1 : (g.M <= 32) ? 2 : 0;
-  const int64_t bm = g.cfg == 2 ? 32 : 128, bn = g.cfg == 1 ? 32 : 128;
+  // tile shapes: 0 128x128, 1 128x32, 2 32x128, 5 128x64, 6 64x128 (3 and 4 are the skinny kernel)
+  g.cfg = (g.N <= 32) ? 1 : (g.M <= 32) ? 2 : (g.N <= 64) ? 5 : (g.M <= 64) ? 6 : 0;
+  const int64_t bm = g.cfg == 2 ? 32 : g.cfg == 6 ? 64 : 128, bn = g.cfg == 1 ? 32 : g.cfg == 5 ? 64 : 128;
   const int64_t tiles = g.B * ((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
   g.splits = 1;
   if (tiles < p.sm_count && g.K >= 1024) {
@@ -427,7 +430,8 @@ static cudaError_t launch_cfg(const ExecCtx& c, const Launch& l, const GemmDev& 
   }
   const int64_t tilesM = (g.M + Cfg::BM - 1) / Cfg::BM, tilesN = (g.N + Cfg::BN - 1) / Cfg::BN;
   const int64_t total = g.B * tilesM * tilesN * g.splits;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(total, p.sm_count));
+  const int ctas_per_sm = (Cfg::BM * Cfg::BN <= 128 * 64) ? 2 : 1;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(total, (int64_t)p.sm_count * ctas_per_sm));
   kern<<<grid, kGemmThreads, Cfg::SMEM, c.stream>>>(p.d_steps, p.d_gemms, l.first_step, dev_state(c));
   return cudaGetLastError();
 }
@@ -457,7 +461,9 @@ cudaError_t launch_gemm(const ExecCtx& c, const Launch& l, bool a_aligned, bool 
   switch (g.cfg) {
     case 0: return launch_layouts<Cfg128x128>(c, l, g, la, lb);
     case 1: return launch_layouts<Cfg128x32>(c, l, g, la, lb);
-    default: return launch_layouts<Cfg32x128>(c, l, g, la, lb);
+    case 2: return launch_layouts<Cfg32x128>(c, l, g, la, lb);
+    case 5: return launch_layouts<Cfg128x64>(c, l, g, la, lb);
+    default: return launch_layouts<Cfg64x128>(c, l, g, la, lb);
   }
 }
 

@@ -408,7 +408,15 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
       p.modes.insert(p.modes.end(), ls.k_modes.begin(), ls.k_modes.end());
       sd.kind = (ls.tiny && allow_interp) ? kInterp : kGeneric;
       if (sd.kind == kGeneric && allow_gemm && ls.has_gemm) {
-        if (gemm_supported(p, sd, ls.gemm)) {
+        if (int sk = skinny_config(p, sd, ls.gemm)) {
+          sd.kind = kGemm;
+          sd.gemm_off = (int32_t)p.gemms.size();
+          ls.gemm.cfg = sk;
+          ls.gemm.splits = 1;
+          ls.gemm.la = ls.gemm.lb = 0;
+          ls.gemm.scratch_off = 0;
+          p.gemms.push_back(ls.gemm);
+        } else if (gemm_supported(p, sd, ls.gemm)) {
           sd.kind = kGemm;
           sd.gemm_off = (int32_t)p.gemms.size();
           gemm_configure(p, ls.gemm);
@@ -698,7 +706,8 @@ static int execute_impl(const ctn_plan* plan, const void* const* operands, void*
       case kGemm: {
         const StepDev& gs = p.steps[l.first_step];
         const bool a_al = ((uintptr_t)ptrs[gs.in_slot[0]] & 15) == 0, b_al = ((uintptr_t)ptrs[gs.in_slot[1]] & 15) == 0;
-        e = p.dtype == CTN_F32 ? launch_gemm_tf32(ctx, l, a_al, b_al) : launch_gemm(ctx, l, a_al, b_al);
+        if (p.gemms[gs.gemm_off].cfg == 3 || p.gemms[gs.gemm_off].cfg == 4) e = launch_skinny(ctx, l);
+        else e = p.dtype == CTN_F32 ? launch_gemm_tf32(ctx, l, a_al, b_al) : launch_gemm(ctx, l, a_al, b_al);
         break;
       }
       case kGemmReduce: e = launch_gemm_reduce(ctx, l); break;

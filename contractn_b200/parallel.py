@@ -33,26 +33,29 @@ def _world(group=None):
 def merge_batch_shards(T_local, c_local, group=None):
     """Global split-format pair for a batch-sharded evaluation.
 
-    ``T_local`` is this rank's shard of the output (mean |T_local| == 1),
-    ``c_local`` its log-scale: a 0-d/1-element float64 tensor (only element 0 is
-    read).  Returns ``(T_shard, c)`` with ONE log-scale ``c`` shared by all ranks
-    such that the concatenation of the shards has mean-abs 1, exactly what the
-    reference returns for the unsharded network.
+    ``T_local`` is this rank's shard of the output, ``c_local`` its log-scale: a
+    0-d/1-element float64 tensor (only element 0 is read).  Returns
+    ``(T_shard, c)`` with ONE log-scale ``c`` shared by all ranks such that the
+    concatenation of the shards has mean-abs 1, exactly what the reference
+    returns for the unsharded network.  One small all-gather (3 doubles per
+    rank) is the only communication.
     """
     c_local = c_local.reshape(-1)[0].to(torch.float64)
     if _world(group) == 1:
         return T_local, c_local.reshape(1)
-    c_star = c_local.clone()
-    dist.all_reduce(c_star, op=dist.ReduceOp.MAX, group=group)
-    w = torch.exp(c_local - c_star)
-    n_local = float(T_local.numel())
+    world = _world(group)
     # sum|T_local| is numel when the shard was rescaled by its last step, but a
     # shard whose norms fall under the reference's 1e-7 threshold is returned
-    # unscaled (contractn/einsum.py:102), so measure it
-    abs_sum = T_local.abs().sum().to(torch.float64)
-    stats = torch.stack([abs_sum * w, torch.full_like(w, n_local)])
-    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-    kappa = stats[0] / stats[1]
+    # unscaled (contractn/einsum.py:102), so measure it (one reduction pass)
+    abs_sum = torch.linalg.vector_norm(T_local.reshape(-1), ord=1).to(torch.float64)
+    mine = torch.stack([c_local, abs_sum, torch.full_like(c_local, float(T_local.numel()))])
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)  # (gloo has no all_gather_into_tensor)
+    table = torch.stack(parts)
+    c_star = table[:, 0].max()
+    w_all = torch.exp(table[:, 0] - c_star)
+    kappa = (table[:, 1] * w_all).sum() / table[:, 2].sum()
+    w = torch.exp(c_local - c_star)
     T = T_local * (w / kappa).to(T_local.dtype)
     return T, (c_star + torch.log(kappa)).reshape(1)
 
@@ -105,36 +108,43 @@ def _parse(einstr):
     return ins.split(","), out
 
 
+def _sliced_flops(step_labels, size, chosen):
+    """Path FLOPs of ONE slice (opt_einsum convention) with `chosen` labels fixed."""
+    total = 0
+    for all_labels, summed in step_labels:
+        vol = 1
+        for s in all_labels:
+            if s not in chosen:
+                vol *= size[s]
+        total += vol * (2 if any(s not in chosen for s in summed) else 1)
+    return total
+
+
 def choose_slice_labels(einstr, shapes, contraction_list, min_slices):
     """Pick contracted bonds to slice until there are at least ``min_slices``
-    slices: repeatedly take the label that carries the most weight in the
-    largest intermediates of the given path ("the largest contracted bonds")."""
+    slices.  Greedy and path-aware: at every round take the label whose removal
+    leaves the cheapest sliced path (total work = slices x per-slice FLOPs of the
+    SAME pairwise sequence), i.e. the bond that lives in the most expensive
+    steps -- "index slicing of the largest contracted bonds"."""
     terms, out = _parse(einstr)
     size = {}
     for t, shp in zip(terms, shapes):
         for s, d in zip(t, shp):
             size[s] = max(size.get(s, 1), int(d))
-    inter = [c[2].split("->")[1] for c in contraction_list[:-1]] or [c[2].split("->")[0] for c in contraction_list]
+    step_labels = []
+    for c in contraction_list:
+        ins = c[2].split("->")[0]
+        step_labels.append((set(ins.replace(",", "")), set(c[1])))
+    candidates = [s for s in size if s not in out and size[s] > 1]
     chosen, n = [], 1
-    while n < min_slices:
-        score = {}
-        for lab in inter:
-            vol = 1.0
-            for s in lab:
-                if s not in chosen:
-                    vol *= size[s]
-            for s in set(lab):
-                if s not in chosen and s not in out and size[s] > 1:
-                    score[s] = score.get(s, 0.0) + vol
-        if not score:
-            # nothing left in the intermediates: fall back to any contracted label
-            rest = [s for s in size if s not in out and s not in chosen and size[s] > 1]
-            if not rest:
-                break
-            best = max(rest, key=lambda s: (size[s], s))
-        else:
-            best = max(score, key=lambda s: (score[s], s))
+    while n < min_slices and candidates:
+        best, best_cost = None, None
+        for s in candidates:
+            cost = _sliced_flops(step_labels, size, set(chosen) | {s}) * n * size[s]
+            if best_cost is None or cost < best_cost or (cost == best_cost and s < best):
+                best, best_cost = s, cost
         chosen.append(best)
+        candidates.remove(best)
         n *= size[best]
     return tuple(chosen)
 

@@ -35,6 +35,12 @@ CASES = [
     ("ab,bc->ac", [(40, 5000), (5000, 30)], "small output, long K: split-K"),
     ("aab,bc->ac", [(20, 20, 64), (64, 30)], "diagonal of an operand"),
     ("ab,bc->ac", [(64, 1), (300, 50)], "broadcast summed index -> not a GEMM, generic"),
+    ("ab,bc->ac", [(4100, 40), (40, 24)], "skinny: rows from the left operand"),
+    ("ab,bc->ac", [(24, 40), (40, 4100)], "skinny: rows from the right operand"),
+    ("abcdef,efxy->abcdxy", [(6, 7, 8, 9, 4, 5), (4, 5, 3, 2)], "skinny: PEPS absorb, summed legs last"),
+    ("abefcd,efxy->abxycd", [(9, 8, 4, 5, 7, 6), (4, 5, 3, 2)], "skinny: summed legs mid-tensor, output interleaved"),
+    ("xe,abcde->abcdx", [(5, 6), (8, 8, 8, 8, 6)], "skinny swapped, single summed leg"),
+    ("ab,bc->ac", [(3000, 7), (7, 64)], "skinny: N = 64 accumulators"),
 ]
 
 
@@ -57,6 +63,7 @@ def test_gemm_kinds_are_selected(gpu_engine):
     assert kinds("ab,bc->ac", [(256, 128), (128, 192)]) == ("gemm", "finalize")
     assert kinds("ab,ab->", [(300, 400)] * 2) == ("gemm", "gemm_reduce", "finalize")
     assert kinds("bps,bp->bs", [(300, 2, 64), (300, 2)]) == ("generic", "finalize")
+    assert kinds("ab,bc->ac", [(4100, 40), (40, 24)]) == ("gemm", "finalize")  # skinny variant
 
 
 def test_gemm_on_strided_views_and_misaligned_pointers(gpu_engine):
