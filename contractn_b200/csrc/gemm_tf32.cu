@@ -377,6 +377,12 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       const int64_t ro = rowA[r];
       const int64_t co = offCb + rowC[r];
       const int n_hi = nk < kHiAcc ? nk : kHiAcc;
+      // All MMAs of this tile have completed (accum_bar), so the pipeline stages are idle:
+      // use stage 0 as a per-warp 32 x 33 transpose buffer and write C with 32 consecutive
+      // columns per instruction (a thread owns a ROW of the accumulator; writing its row
+      // directly would scatter 4-byte pieces over 32 rows per instruction).
+      float* tbuf = reinterpret_cast<float*>(tiles) + warp * (32 * 33);
+      float local_f = 0.f;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = h * 64 + cc * 32;
@@ -399,17 +405,26 @@ __global__ void __launch_bounds__(kThreadsT, 1)
           tc_fence_before();
           mbar_arrive(tmem_empty_bar);
         }
-        if (ro >= 0) {
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = col0 + j;
-            if (colB[c] < 0) continue;
-            const float v = sum[j] * alpha;
-            C[co + colC[c]] = v;
-            local_abs += fabs((double)v);
+        for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = sum[j] * alpha;
+        __syncwarp();
+        // lane <-> column: row i of this warp's block, column col0 + lane
+        const int64_t cbase = colC[col0 + lane];
+        const bool col_ok = colB[col0 + lane] >= 0;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int ri = q * 32 + i;
+          if (rowA[ri] >= 0 && col_ok) {
+            const float v = tbuf[i * 33 + lane];
+            C[offCb + rowC[ri] + cbase] = v;
+            local_f += fabsf(v);
           }
         }
       }
+      local_abs += (double)local_f;
+      (void)ro;
+      (void)co;
     } else {
       // ================= MMA issuer (warp 8) =================
       if (tile_iter > 0) {
