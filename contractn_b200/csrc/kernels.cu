@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kThreads) generic_step_kernel(const StepDev* _
 // and its threads run along the innermost mode, so loads and stores are
 // coalesced whenever that mode is contiguous and no div/mod is left in the loop.
 constexpr int kRowsKTable = 512;  // summed-mode offsets kept in shared memory up to this many
+constexpr int kRowsPerItem = 4;
 
 template <typename T, int NIN, typename ACC>
 __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* __restrict__ steps,
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* _
                                                                 DevState d) {
   __shared__ double red[33];
   __shared__ bool last_block;
-  __shared__ int64_t row_base[NIN];
+  __shared__ int64_t row_base[kRowsPerItem][NIN];
   __shared__ int64_t k_off[NIN][kRowsKTable];
   const StepDev& s = steps[step_idx];
   const ModeDev* modes = all_modes + s.mode_off;
@@ -166,7 +167,6 @@ __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* _
   const int64_t inner_n = inner.extent;
   const int64_t n_rows = s.out_numel / inner_n;
   const int64_t chunks = (inner_n + kThreads - 1) / kThreads;
-  const int64_t work = n_rows * chunks;
   const int kn = (int)s.k_numel;  // <= kRowsKTable (checked by the launcher)
   const int n_k_modes = s.n_k_modes, n_outer = s.n_out_modes - 1;
   const ModeDev* km = modes + s.n_out_modes;
@@ -191,43 +191,62 @@ __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* _
   for (int i = 0; i < NIN; ++i) inner_stride[i] = inner.stride[i];
   const ACC alpha_t = (ACC)alpha;
 
+  // a work item is kRowsPerItem consecutive rows x one 256-wide chunk of the inner mode: several
+  // rows per barrier pair, and their loads are all in flight before the first result is needed
   double local = 0.0;
-  for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
-    const int64_t row = w / chunks, chunk = w - row * chunks;
+  const int64_t row_groups = (n_rows + kRowsPerItem - 1) / kRowsPerItem;
+  const int64_t work_items = row_groups * chunks;
+  for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+    const int64_t rg = w / chunks, chunk = w - rg * chunks;
+    const int64_t row0 = rg * kRowsPerItem;
     __syncthreads();
-    if (threadIdx.x < NIN) {
-      int64_t o = 0, rem = row;
+    if (threadIdx.x < NIN * kRowsPerItem) {
+      const int i = threadIdx.x % NIN, rr = threadIdx.x / NIN;
+      int64_t o = 0, rem = row0 + rr;
       for (int m = n_outer - 1; m >= 0; --m) {
         const int64_t e = modes[m].extent;
         const int64_t idx = rem % e;
         rem /= e;
-        o += idx * modes[m].stride[threadIdx.x];
+        o += idx * modes[m].stride[i];
       }
-      row_base[threadIdx.x] = o;
+      row_base[rr][i] = o;
     }
     __syncthreads();
     const int64_t j = chunk * kThreads + threadIdx.x;
     if (j < inner_n) {
-      const T* p[NIN];
-#pragma unroll
-      for (int i = 0; i < NIN; ++i) p[i] = in[i] + row_base[i] + j * inner_stride[i];
-      ACC acc;
+      ACC acc[kRowsPerItem];
       if (n_k_modes == 0) {
-        acc = (ACC)1;
 #pragma unroll
-        for (int i = 0; i < NIN; ++i) acc *= (ACC)__ldg(p[i]);
+        for (int rr = 0; rr < kRowsPerItem; ++rr) {
+          acc[rr] = (ACC)1;
+          if (row0 + rr < n_rows) {
+#pragma unroll
+            for (int i = 0; i < NIN; ++i) acc[rr] *= (ACC)__ldg(in[i] + row_base[rr][i] + j * inner_stride[i]);
+          }
+        }
       } else {
-        acc = (ACC)0;
-        for (int k = 0; k < kn; ++k) {
-          ACC pr = (ACC)__ldg(p[0] + k_off[0][k]);
 #pragma unroll
-          for (int i = 1; i < NIN; ++i) pr *= (ACC)__ldg(p[i] + k_off[i][k]);
-          acc += pr;
+        for (int rr = 0; rr < kRowsPerItem; ++rr) acc[rr] = (ACC)0;
+        for (int k = 0; k < kn; ++k) {
+#pragma unroll
+          for (int rr = 0; rr < kRowsPerItem; ++rr) {
+            if (row0 + rr < n_rows) {
+              ACC pr = (ACC)__ldg(in[0] + row_base[rr][0] + j * inner_stride[0] + k_off[0][k]);
+#pragma unroll
+              for (int i = 1; i < NIN; ++i) pr *= (ACC)__ldg(in[i] + row_base[rr][i] + j * inner_stride[i] + k_off[i][k]);
+              acc[rr] += pr;
+            }
+          }
         }
       }
-      const T r = (T)(acc * alpha_t);
-      out[row * inner_n + j] = r;
-      local += (double)fabs(r);
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerItem; ++rr) {
+        if (row0 + rr < n_rows) {
+          const T r = (T)(acc[rr] * alpha_t);
+          out[(row0 + rr) * inner_n + j] = r;
+          local += (double)fabs(r);
+        }
+      }
     }
   }
   const double bsum = block_sum(local, red);
@@ -279,7 +298,8 @@ cudaError_t launch_generic(const ExecCtx& c, const Launch& l) {
   if (s.n_out_modes >= 1 && s.k_numel <= kRowsKTable && s.n_in <= 4) {
     const int64_t inner_n = p.modes[s.mode_off + s.n_out_modes - 1].extent;
     if (inner_n >= 64) {
-      const int64_t work = (s.out_numel / inner_n) * ((inner_n + kThreads - 1) / kThreads);
+      const int64_t n_rows = s.out_numel / inner_n;
+      const int64_t work = ((n_rows + kRowsPerItem - 1) / kRowsPerItem) * ((inner_n + kThreads - 1) / kThreads);
       const int grid = (int)std::max<int64_t>(1, std::min(work, cap));
       // float data: short sums stay in fp32 (what the reference's einsum does too);
       // long ones are accumulated in fp64
