@@ -209,42 +209,56 @@ __device__ __forceinline__ void chunk_sources(const float* (&src)[ChunkCount<LAY
 }
 
 // ---- producer: global -> raw tile (asynchronous) ----
+// soff[i] / kk[i]: shared-memory byte offset and k-offset-in-block of this thread's i-th chunk
+// (functions of the thread index only: computed once per kernel).
 template <int LAYOUT>
 __device__ __forceinline__ void issue_copy(uint32_t raw_tile, const float* const (&src)[ChunkCount<LAYOUT>::N],
-                                           const KInfo& ki, int64_t k0, int64_t K, int t) {
+                                           const int (&soff)[ChunkCount<LAYOUT>::N], const int (&kk)[ChunkCount<LAYOUT>::N],
+                                           const KInfo& ki, int64_t k0, int64_t K, bool interior) {
+  if (interior && ki.n == 1) {
+    // every row of the tile exists and the whole k-block is inside K: no predicates
+    const int64_t sk = ki.s[0];
+#pragma unroll
+    for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i) {
+      const float* p = src[i] + (k0 + kk[i]) * sk;
+      if (LAYOUT == kAnyLayout) cp_async4(raw_tile + soff[i], p, true);
+      else cp_async16(raw_tile + soff[i], p, true);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i) {
-    int row, kk;
-    const int off = chunk_offset<LAYOUT>(i, t, row, kk);
-    const int64_t k = k0 + kk;
+    const int64_t k = k0 + kk[i];
     const bool valid = src[i] != nullptr && k < K;
     const float* p = valid ? src[i] + ki.off(k) : src[0];
-    if (LAYOUT == kAnyLayout) cp_async4(raw_tile + off, p, valid);
-    else cp_async16(raw_tile + off, p, valid);
+    if (LAYOUT == kAnyLayout) cp_async4(raw_tile + soff[i], p, valid);
+    else cp_async16(raw_tile + soff[i], p, valid);
   }
 }
 
 __device__ __forceinline__ float residual_tf32(float x) {
-  const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);  // what the tensor core will use
-  const float lo = x - hi;                                             // exact in fp32
-  // round the residual to tf32 ourselves (nearest): the core's truncation is then a no-op
-  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xffffe000u);
+  // what the tensor core will use as `hi` is trunc(x); the residual is exact in fp32.  (The core
+  // truncates the residual to tf32 as well: a relative error below 2^-22 of x, not worth the two
+  // extra instructions per element a round-to-nearest would cost in this issue-bound loop.)
+  return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
 
 // ---- producer: raw tile -> lo tile (each thread revisits the chunks it copied) ----
 template <int LAYOUT>
-__device__ __forceinline__ void make_lo(const unsigned char* raw_tile, unsigned char* lo_tile, int t) {
+__device__ __forceinline__ void make_lo(const unsigned char* raw_tile, unsigned char* lo_tile,
+                                        const int (&soff)[ChunkCount<LAYOUT>::N]) {
+  if (LAYOUT == kAnyLayout) {
 #pragma unroll
-  for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i) {
-    int row, kk;
-    const int off = chunk_offset<LAYOUT>(i, t, row, kk);
-    if (LAYOUT == kAnyLayout) {
-      *reinterpret_cast<float*>(lo_tile + off) = residual_tf32(*reinterpret_cast<const float*>(raw_tile + off));
-    } else {
-      const float4 x = *reinterpret_cast<const float4*>(raw_tile + off);
-      *reinterpret_cast<float4*>(lo_tile + off) =
-          make_float4(residual_tf32(x.x), residual_tf32(x.y), residual_tf32(x.z), residual_tf32(x.w));
-    }
+    for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i)
+      *reinterpret_cast<float*>(lo_tile + soff[i]) = residual_tf32(*reinterpret_cast<const float*>(raw_tile + soff[i]));
+  } else {
+    float4 x[ChunkCount<LAYOUT>::N];
+#pragma unroll
+    for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i) x[i] = *reinterpret_cast<const float4*>(raw_tile + soff[i]);
+#pragma unroll
+    for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i)
+      *reinterpret_cast<float4*>(lo_tile + soff[i]) =
+          make_float4(residual_tf32(x[i].x), residual_tf32(x[i].y), residual_tf32(x[i].z), residual_tf32(x[i].w));
   }
 }
 
@@ -306,6 +320,17 @@ __global__ void __launch_bounds__(kThreadsT, 1)
                          ((LB == kMNFast ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
   const KInfo kinfo_a = load_kinfo(g, false), kinfo_b = load_kinfo(g, true);
+  int soffA[ChunkCount<LA>::N], kkA[ChunkCount<LA>::N], soffB[ChunkCount<LB>::N], kkB[ChunkCount<LB>::N];
+#pragma unroll
+  for (int i = 0; i < ChunkCount<LA>::N; ++i) {
+    int row;
+    soffA[i] = chunk_offset<LA>(i, threadIdx.x & (kProducerThreads - 1), row, kkA[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < ChunkCount<LB>::N; ++i) {
+    int row;
+    soffB[i] = chunk_offset<LB>(i, threadIdx.x & (kProducerThreads - 1), row, kkB[i]);
+  }
   double local_abs = 0.0;
   uint32_t it_base = 0;   // k-blocks issued so far by this CTA (stage / phase bookkeeping)
   uint32_t tile_iter = 0;
@@ -344,12 +369,14 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       const float* srcB[ChunkCount<LB>::N];
       chunk_sources<LA>(srcA, A + offAb, rowA, tid);
       chunk_sources<LB>(srcB, Bp + offBb, colB, tid);
+      const bool rows_full = (tm + 1) * BM <= M && (tn + 1) * BN <= N;
       auto prefetch = [&](int kb) {
         const uint32_t it = it_base + kb, st = it % kStagesT, ph = (it / kStagesT) & 1u;
         mbar_wait(empty_bar(st), ph ^ 1u);  // the tensor core has finished reading this stage
         const uint32_t stage = smem_u32(tiles + st * STAGE_BYTES);
-        issue_copy<LA>(stage, srcA, kinfo_a, (int64_t)kb * BKF, K, tid);
-        issue_copy<LB>(stage + 2 * SUB_BYTES, srcB, kinfo_b, (int64_t)kb * BKF, K, tid);
+        const bool interior = rows_full && (int64_t)(kb + 1) * BKF <= K;
+        issue_copy<LA>(stage, srcA, soffA, kkA, kinfo_a, (int64_t)kb * BKF, K, interior);
+        issue_copy<LB>(stage + 2 * SUB_BYTES, srcB, soffB, kkB, kinfo_b, (int64_t)kb * BKF, K, interior);
       };
 #pragma unroll
       for (int j = 0; j < kStagesT - 1; ++j) {
@@ -360,8 +387,8 @@ __global__ void __launch_bounds__(kThreadsT, 1)
         cp_async_wait<kStagesT - 2>();  // this thread's chunks of k-block kb have landed
         const uint32_t it = it_base + kb, st = it % kStagesT;
         unsigned char* stage = tiles + st * STAGE_BYTES;
-        make_lo<LA>(stage, stage + SUB_BYTES, tid);
-        make_lo<LB>(stage + 2 * SUB_BYTES, stage + 3 * SUB_BYTES, tid);
+        make_lo<LA>(stage, stage + SUB_BYTES, soffA);
+        make_lo<LB>(stage + 2 * SUB_BYTES, stage + 3 * SUB_BYTES, soffB);
         fence_proxy_async();
         mbar_arrive(full_bar(st));
         if (kb + kStagesT - 1 < nk) prefetch(kb + kStagesT - 1);
