@@ -89,8 +89,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
@@ -410,22 +410,32 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       // directly would scatter 4-byte pieces over 32 rows per instruction).
       float* tbuf = reinterpret_cast<float*>(tiles) + warp * (32 * 33);
       float local_f = 0.f;
+      // this lane's own row: C offset (or -1), handed to the other lanes by shuffle below
+      const int64_t my_ro = rowA[q * 32 + lane] >= 0 ? offCb + rowC[q * 32 + lane] : -1;
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = h * 64 + cc * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
         float sum[32];
         {
-          uint32_t acc[32];
-          tc_ld32(taddr + (uint32_t)kHiAcc * BN, acc);  // corrections first (smallest)
+          // corrections + first hi accumulator in flight together, then the other two
+          uint32_t a0[32], a1[32];
+          tc_ld32(taddr + (uint32_t)kHiAcc * BN, a0);
+          tc_ld32(taddr, a1);
+          tc_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(acc[j]);
-        }
-        for (int a = n_hi - 1; a >= 0; --a) {
-          uint32_t acc[32];
-          tc_ld32(taddr + (uint32_t)a * BN, acc);
+          for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(a0[j]) + __uint_as_float(a1[j]);
+          if (n_hi > 1) {
+            tc_ld32(taddr + (uint32_t)BN, a0);
+            if (n_hi > 2) tc_ld32(taddr + 2u * BN, a1);
+            tc_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(acc[j]);
+            for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(a0[j]);
+            if (n_hi > 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(a1[j]);
+            }
+          }
         }
         if (cc == 1) {
           // accumulators fully read: the MMA warp may start the next tile
@@ -439,12 +449,12 @@ __global__ void __launch_bounds__(kThreadsT, 1)
         // lane <-> column: row i of this warp's block, column col0 + lane
         const int64_t cbase = colC[col0 + lane];
         const bool col_ok = colB[col0 + lane] >= 0;
-#pragma unroll 8
+#pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int ri = q * 32 + i;
-          if (rowA[ri] >= 0 && col_ok) {
-            const float v = tbuf[i * 33 + lane];
-            C[offCb + rowC[ri] + cbase] = v;
+          const int64_t ro_i = __shfl_sync(0xffffffffu, my_ro, i);
+          const float v = tbuf[i * 33 + lane];
+          if (ro_i >= 0 && col_ok) {
+            C[ro_i + cbase] = v;
             local_f += fabsf(v);
           }
         }
