@@ -39,6 +39,7 @@ struct ModeDev {
 struct GemmMode {
   int64_t extent;
   int64_t sa, sb, sc;
+  int64_t sw;  // stride in the fused consumer's weight operand (0 unless fuse_pr > 0)
 };
 constexpr int kGemmMaxModes = 12;  // per group, after fusion
 
@@ -53,6 +54,13 @@ struct GemmDev {
   int32_t splits;       // split-K factor (1 = single pass)
   int32_t la, lb;       // shared-memory staging layout of A and B
   int64_t scratch_off;  // split-K partial tiles, byte offset in the arena
+  // fused consumer (gemm_tf32.cu): the GEMM result X[m, (r, n')] is never written; the next step
+  // out[m, n'] = sum_r W[m, r] * X[m, (r, n')] is evaluated in the epilogue (in_slot[2] = W).
+  // `n` then holds only the n' modes (sc = strides in `out`), N = prod(n'), and:
+  int32_t fuse_pr;      // extent of r (0 = not fused; 2 or 4)
+  int32_t fuse_pad;
+  int64_t fuse_sb;      // stride of r in B
+  int64_t fuse_sw;      // stride of r in W
 };
 
 // Device-side description of one step.

@@ -39,7 +39,7 @@ constexpr int STAGE_BYTES = 4 * SUB_BYTES;  // 64 KB
 constexpr int TMEM_COLS = 512;  // 3 hi*hi accumulators (k-blocks round-robin) + 1 for the hi*lo / lo*hi corrections
 constexpr int kHiAcc = 3;
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)kStagesT * STAGE_BYTES +
-                              4 * 128 * sizeof(int64_t) + 16 * sizeof(uint64_t) + 64 + 40 * sizeof(double);
+                              5 * 128 * sizeof(int64_t) + 16 * sizeof(uint64_t) + 64 + 40 * sizeof(double);
 
 enum : int32_t { kKFast = 0, kMNFast = 1, kAnyLayout = 2 };
 
@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   int64_t* colB = rowA + BM;
   int64_t* rowC = colB + BN;
   int64_t* colC = rowC + BM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(colC + BN);  // full[3], empty[3], accum, tmem_empty
+  int64_t* rowW = colC + BN;  // fused consumer: offset of the row in the weight operand
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowW + BM);  // full[3], empty[3], accum, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   double* red = reinterpret_cast<double*>(tmem_slot + 16);
   __shared__ bool last_block;
@@ -285,7 +286,10 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   float* C = (float*)d.ptrs[s.out_slot];
   const float alpha = (float)(d.inv_kappa[s.in_slot[0]] * d.inv_kappa[s.in_slot[1]]);
   const int64_t M = g.M, N = g.N, K = g.K;
-  const int64_t tilesM = (M + BM - 1) / BM, tilesN = (N + BN - 1) / BN;
+  // fused consumer: the 128 accumulator columns of a tile are pr blocks (one per value of the
+  // summed index r) of npt consecutive n' each; otherwise 128 consecutive n
+  const int pr = g.fuse_pr, npt = pr ? BN / pr : BN;
+  const int64_t tilesM = (M + BM - 1) / BM, tilesN = (N + npt - 1) / npt;
   const int64_t total = g.B * tilesM * tilesN;
   const int nk = (int)((K + BKF - 1) / BKF);
 
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     int row;
     soffB[i] = chunk_offset<LB>(i, threadIdx.x & (kProducerThreads - 1), row, kkB[i]);
   }
-  double local_abs = 0.0;
+  double local_abs = 0.0, local_abs_t = 0.0;  // sum|out| and (fused) sum|X|
   uint32_t it_base = 0;   // k-blocks issued so far by this CTA (stage / phase bookkeeping)
   uint32_t tile_iter = 0;
 
@@ -352,14 +356,30 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       for (int r = tid; r < BM; r += kProducerThreads) {
         const int64_t m = tm * BM + r;
         int64_t oa = -1, oc = 0;
-        if (m < M) group_offsets(g.m, g.n_m, m, false, oa, oc);
+        int64_t ow = 0;
+        if (m < M) {
+          group_offsets(g.m, g.n_m, m, false, oa, oc);
+          if (pr) {
+            int64_t idx = m;
+            for (int i = g.n_m - 1; i >= 0; --i) {
+              const int64_t e = g.m[i].extent, qq = idx / e;
+              ow += (idx - qq * e) * g.m[i].sw;
+              idx = qq;
+            }
+          }
+        }
         rowA[r] = oa;
         rowC[r] = oc;
+        rowW[r] = ow;
       }
       for (int r = tid; r < BN; r += kProducerThreads) {
-        const int64_t n = tn * BN + r;
+        const int rr = pr ? r / npt : 0;
+        const int64_t n = pr ? tn * npt + (r - rr * npt) : tn * BN + r;
         int64_t ob = -1, oc = 0;
-        if (n < N) group_offsets(g.n, g.n_n, n, true, ob, oc);
+        if (n < N) {
+          group_offsets(g.n, g.n_n, n, true, ob, oc);
+          ob += (int64_t)rr * g.fuse_sb;
+        }
         colB[r] = ob;
         colC[r] = oc;
       }
@@ -369,7 +389,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       const float* srcB[ChunkCount<LB>::N];
       chunk_sources<LA>(srcA, A + offAb, rowA, tid);
       chunk_sources<LB>(srcB, Bp + offBb, colB, tid);
-      const bool rows_full = (tm + 1) * BM <= M && (tn + 1) * BN <= N;
+      const bool rows_full = (tm + 1) * BM <= M && (tn + 1) * npt <= N;
       auto prefetch = [&](int kb) {
         const uint32_t it = it_base + kb, st = it % kStagesT, ph = (it / kStagesT) & 1u;
         mbar_wait(empty_bar(st), ph ^ 1u);  // the tensor core has finished reading this stage
@@ -408,10 +428,72 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       // use stage 0 as a per-warp 32 x 33 transpose buffer and write C with 32 consecutive
       // columns per instruction (a thread owns a ROW of the accumulator; writing its row
       // directly would scatter 4-byte pieces over 32 rows per instruction).
-      float* tbuf = reinterpret_cast<float*>(tiles) + warp * (32 * 33);
       float local_f = 0.f;
       // this lane's own row: C offset (or -1), handed to the other lanes by shuffle below
       const int64_t my_ro = rowA[q * 32 + lane] >= 0 ? offCb + rowC[q * 32 + lane] : -1;
+      if (pr) {
+        // ---- fused consumer: out[m, n'] = sum_r W[m, r] * X[m, (r, n')], X never leaves the SM ----
+        const int cpr = npt / 32;  // 32-column chunks per value of r
+        float* tq = reinterpret_cast<float*>(tiles) + q * (4 * 32 * 33);  // 4 blocks of 32 x 33 per row quarter
+        const float* Wp = (const float*)d.ptrs[s.in_slot[2]];
+        const float alpha_w = (float)d.inv_kappa[s.in_slot[2]];
+        const bool row_ok = rowA[q * 32 + lane] >= 0;
+        const int64_t wro = rowW[q * 32 + lane];
+        float local_t = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col0 = h * 64 + cc * 32;
+          const int rr = col0 / npt, nc = (col0 - rr * npt) >> 5, blk = rr * cpr + nc;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+          float sum[32];
+          {
+            uint32_t a0[32], a1[32];
+            tc_ld32(taddr + (uint32_t)kHiAcc * BN, a0);
+            tc_ld32(taddr, a1);
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = __uint_as_float(a0[j]) + __uint_as_float(a1[j]);
+            if (n_hi > 1) {
+              tc_ld32(taddr + (uint32_t)BN, a0);
+              if (n_hi > 2) tc_ld32(taddr + 2u * BN, a1);
+              tc_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(a0[j]);
+              if (n_hi > 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(a1[j]);
+              }
+            }
+          }
+          if (cc == 1) {
+            tc_fence_before();
+            mbar_arrive(tmem_empty_bar);
+          }
+          // rows / columns outside the problem were zero-filled, so their sums are exact zeros
+          const float w = row_ok ? __ldg(Wp + wro + (int64_t)rr * g.fuse_sw) * alpha_w : 0.f;
+          float* blk_p = tq + blk * (32 * 33) + lane * 33;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = sum[j] * alpha;  // the un-materialised X entry
+            local_t += fabsf(t);
+            blk_p[j] = t * w;
+          }
+        }
+        local_abs_t += (double)local_t;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // the two warps sharing this row quarter
+        for (int idx = h; idx < cpr * 32; idx += 2) {
+          const int nc = idx >> 5, i = idx & 31;
+          float v = 0.f;
+          for (int rr = 0; rr < pr; ++rr) v += tq[(rr * cpr + nc) * (32 * 33) + i * 33 + lane];
+          const int64_t ro_i = __shfl_sync(0xffffffffu, my_ro, i);
+          const int c = nc * 32 + lane;
+          if (ro_i >= 0 && colB[c] >= 0) {
+            C[ro_i + colC[c]] = v;
+            local_f += fabsf(v);
+          }
+        }
+      } else {
+      float* tbuf = reinterpret_cast<float*>(tiles) + warp * (32 * 33);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = h * 64 + cc * 32;
@@ -458,6 +540,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
             local_f += fabsf(v);
           }
         }
+      }
       }
       local_abs += (double)local_f;
       (void)ro;
@@ -512,8 +595,10 @@ __global__ void __launch_bounds__(kThreadsT, 1)
                  : "memory");
   }
   const double bsum = block_sum(local_abs, red);
+  const double bsum_t = g.fuse_pr ? block_sum(local_abs_t, red) : 0.0;
   if (tid == 0) {
     d.partials[blockIdx.x] = bsum;
+    d.partials[kMaxPartials + blockIdx.x] = bsum_t;
     __threadfence();
     const uint32_t tk = atomicAdd(&d.tickets[s.ticket], 1u);
     last_block = (tk == gridDim.x - 1);
@@ -521,10 +606,20 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   __syncthreads();
   if (last_block) {
     __threadfence();
-    double a2 = 0.0;
-    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) a2 += __ldcg(&d.partials[i]);
+    double a2 = 0.0, a3 = 0.0;
+    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+      a2 += __ldcg(&d.partials[i]);
+      a3 += __ldcg(&d.partials[kMaxPartials + i]);
+    }
     const double norm = block_sum(a2, red);
+    const double norm_x = block_sum(a3, red);
     if (tid == 0) {
+      if (g.fuse_pr) {
+        // the reference stabilises X, then out = X_hat * W: both of its decisions must be "rescale"
+        // for the fused result to be the same up to the gauge (einsum.py:102)
+        const double kappa_x = norm_x / ((double)s.out_numel * g.fuse_pr);
+        if (!(norm_x > kMinNorm) || !(norm / kappa_x > kMinNorm)) d.hdr->flags |= CTN_RESULT_DEGENERATE;
+      }
       record_scale(d, s.out_slot, norm, s.out_numel);
       d.tickets[s.ticket] = 0;
     }

@@ -8,6 +8,7 @@
 // tiny steps into a single-CTA interpreter launch.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -95,6 +96,12 @@ struct LoweredStep {
   bool tiny = false;
   GemmDev gemm;
   bool has_gemm = false;
+  // label-level view, kept for the consumer-fusion pass
+  std::vector<std::vector<int32_t>> in_labels;
+  std::vector<int32_t> out_labels;
+  std::vector<std::pair<int32_t, GemmMode>> gm, gn, gk;  // unfused GEMM groups with their labels
+  int32_t g_n_batch = 0;
+  bool fused_consumer = false;
 };
 
 static void fuse_modes(std::vector<ModeDev>& modes, int n_in, bool out_modes) {
@@ -130,6 +137,7 @@ static void fuse_modes(std::vector<ModeDev>& modes, int n_in, bool out_modes) {
 }
 
 static void fuse_gemm_group(GemmMode* g, int32_t& n, bool keep_order) {
+  // (sw takes part in the compatibility test so that fused-consumer strides stay exact)
   std::vector<GemmMode> kept;
   for (int i = 0; i < n; ++i)
     if (g[i].extent != 1) kept.push_back(g[i]);
@@ -143,9 +151,10 @@ static void fuse_gemm_group(GemmMode* g, int32_t& n, bool keep_order) {
   for (auto& m : kept) {
     if (!fused.empty()) {
       GemmMode& o = fused.back();
-      if (o.sa == m.sa * m.extent && o.sb == m.sb * m.extent && o.sc == m.sc * m.extent) {
+      if (o.sa == m.sa * m.extent && o.sb == m.sb * m.extent && o.sc == m.sc * m.extent &&
+          o.sw == m.sw * m.extent) {
         o.extent *= m.extent;
-        o.sa = m.sa; o.sb = m.sb; o.sc = m.sc;
+        o.sa = m.sa; o.sb = m.sb; o.sc = m.sc; o.sw = m.sw;
         continue;
       }
     }
@@ -205,6 +214,8 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
   ls.out_slot = (int32_t)p.slots.size();
   p.slots.push_back(out);
   live.push_back(ls.out_slot);
+  ls.in_labels = in_labels;
+  ls.out_labels = out.labels;
 
   auto make_mode = [&](int32_t l) {
     ModeDev m{};
@@ -267,16 +278,17 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
     for (int a = 0; a < sd.out_rank; ++a) {
       int32_t l = sd.out_labels[a];
       bool inA = in_stride[0].count(l) > 0, inB = in_stride[1].count(l) > 0;
-      GemmMode m{extent[l], stride_of(0, l), stride_of(1, l), c_stride[l]};
-      if (inA && inB) push(g.batch, g.n_batch, m);
-      else if (inA) push(g.m, g.n_m, m);
-      else push(g.n, g.n_n, m);
+      GemmMode m{extent[l], stride_of(0, l), stride_of(1, l), c_stride[l], 0};
+      if (inA && inB) { push(g.batch, g.n_batch, m); ls.g_n_batch++; }
+      else if (inA) { push(g.m, g.n_m, m); ls.gm.emplace_back(l, m); }
+      else { push(g.n, g.n_n, m); ls.gn.emplace_back(l, m); }
     }
     for (auto& kv : extent) {
       if (out_set.count(kv.first)) continue;
       int32_t l = kv.first;
-      GemmMode m{kv.second, stride_of(0, l), stride_of(1, l), 0};
+      GemmMode m{kv.second, stride_of(0, l), stride_of(1, l), 0, 0};
       push(g.k, g.n_k, m);
+      ls.gk.emplace_back(l, m);
     }
     if (ok) {
       fuse_gemm_group(g.batch, g.n_batch, true);
@@ -293,6 +305,98 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
     }
   }
   return CTN_OK;
+}
+
+// Consumer fusion (float32, tcgen05 path): a GEMM step X[m,(r,n')] = A*B whose result is
+// consumed ONLY by the next step out[m,n'] = sum_r W[m,r] * X[m,(r,n')] (the hyperedge step
+// "bps,bp->bs" of a batched MPS sweep, cfg 3) is merged with it: the GEMM epilogue applies the
+// weights and sums over r, X is never written.  Stabilisation stays exact up to the gauge:
+// the kernel still measures sum|X| and sum|out| and flags CTN_RESULT_DEGENERATE if either of the
+// reference's two rescale decisions (contractn/einsum.py:102) would have been "skip".
+static bool try_fuse_consumer(Plan& p, LoweredStep& cur, const LoweredStep& nxt) {
+  if (p.dtype != CTN_F32 || !cur.has_gemm || cur.tiny || cur.g_n_batch != 0) return false;
+  if (cur.in_slots.size() != 2 || nxt.in_slots.size() != 2 || nxt.elementwise) return false;
+  int xi = nxt.in_slots[0] == cur.out_slot ? 0 : nxt.in_slots[1] == cur.out_slot ? 1 : -1;
+  if (xi < 0 || nxt.in_slots[1 - xi] == cur.out_slot) return false;
+  const int wi = 1 - xi;
+  const std::vector<int32_t>& xl = nxt.in_labels[xi];
+  const std::vector<int32_t>& wl = nxt.in_labels[wi];
+  if (xl != cur.out_labels) return false;
+  std::set<int32_t> xset(xl.begin(), xl.end()), wset(wl.begin(), wl.end()), oset(nxt.out_labels.begin(), nxt.out_labels.end());
+  if (xset.size() != xl.size() || wset.size() != wl.size()) return false;  // no diagonals
+  // exactly one summed label r, carried by W and by the GEMM's N side
+  std::vector<int32_t> summed;
+  for (auto l : xset) if (!oset.count(l)) summed.push_back(l);
+  for (auto l : wset) if (!xset.count(l)) return false;  // W must not bring new labels
+  if (summed.size() != 1 || oset.size() != xset.size() - 1) return false;
+  const int32_t r = summed[0];
+  if (!wset.count(r)) return false;
+  auto find = [](const std::vector<std::pair<int32_t, GemmMode>>& v, int32_t l) -> const GemmMode* {
+    for (auto& kv : v) if (kv.first == l) return &kv.second;
+    return nullptr;
+  };
+  // the summed label may sit on either side of the product: C = A*B is also C^T = B^T * A^T,
+  // which in the strided formulation is just exchanging the operands and their stride fields
+  std::vector<int32_t> ab = cur.in_slots;
+  std::vector<std::pair<int32_t, GemmMode>> gm = cur.gm, gn = cur.gn, gk = cur.gk;
+  if (!find(gn, r) && find(gm, r)) {
+    std::swap(ab[0], ab[1]);
+    std::swap(gm, gn);
+    for (auto* grp : {&gm, &gn, &gk})
+      for (auto& kv : *grp) std::swap(kv.second.sa, kv.second.sb);
+  }
+  const GemmMode* rmode = find(gn, r);
+  if (!rmode || (rmode->extent != 2 && rmode->extent != 4)) return false;
+  for (auto l : wl) if (l != r && !find(gm, l)) return false;  // weights vary with rows only
+  // strides of W and of the fused output
+  const Slot& W = p.slots[nxt.in_slots[wi]];
+  std::map<int32_t, int64_t> sw, sc;
+  for (size_t a = 0; a < wl.size(); ++a) {
+    const GemmMode* wmode = wl[a] == r ? rmode : find(gm, wl[a]);
+    if (W.extents[a] != wmode->extent) return false;  // no broadcasting in the fused form
+    sw[wl[a]] = W.strides[a];
+  }
+  const Slot& O = p.slots[nxt.out_slot];
+  for (size_t a = 0; a < nxt.out_labels.size(); ++a) sc[nxt.out_labels[a]] = O.strides[a];
+  GemmDev g{};
+  for (auto& kv : gm) {
+    if (g.n_m >= kGemmMaxModes) return false;
+    GemmMode m = kv.second;
+    m.sc = sc[kv.first];
+    m.sw = sw.count(kv.first) ? sw[kv.first] : 0;
+    g.m[g.n_m++] = m;
+  }
+  for (auto& kv : gn) {
+    if (kv.first == r) continue;
+    if (g.n_n >= kGemmMaxModes) return false;
+    GemmMode m = kv.second;
+    m.sc = sc[kv.first];
+    g.n[g.n_n++] = m;
+  }
+  for (auto& kv : gk) {
+    if (g.n_k >= kGemmMaxModes) return false;
+    g.k[g.n_k++] = kv.second;
+  }
+  fuse_gemm_group(g.m, g.n_m, true);
+  fuse_gemm_group(g.n, g.n_n, true);
+  fuse_gemm_group(g.k, g.n_k, false);
+  g.B = g.M = g.N = g.K = 1;
+  for (int i = 0; i < g.n_m; ++i) g.M *= g.m[i].extent;
+  for (int i = 0; i < g.n_n; ++i) g.N *= g.n[i].extent;
+  for (int i = 0; i < g.n_k; ++i) g.K *= g.k[i].extent;
+  if (g.M < 16 || g.N < 16 || g.K < 8 || g.n_k > 4) return false;
+  g.fuse_pr = (int32_t)rmode->extent;
+  g.fuse_sb = rmode->sb;
+  g.fuse_sw = sw[r];
+  // merge
+  cur.in_slots = ab;
+  cur.in_slots.push_back(nxt.in_slots[wi]);
+  cur.out_slot = nxt.out_slot;
+  cur.out_numel = nxt.out_numel;
+  cur.flops += nxt.flops;
+  cur.gemm = g;
+  cur.fused_consumer = true;
+  return true;
 }
 
 static void layout_state(Plan& p) {
@@ -370,6 +474,10 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
     }
     lowered.push_back(std::move(ls));
   }
+  if (fuse && !(d.flags & CTN_PLAN_NO_GEMM)) {
+    for (size_t t = 0; t + 1 < lowered.size(); ++t)
+      if (try_fuse_consumer(p, lowered[t], lowered[t + 1])) lowered.erase(lowered.begin() + t + 1);
+  }
   if (live.size() != 1) return CTN_ERR_INVALID;  // the list must reduce to one tensor
   p.final_slot = live[0];
   p.slots[p.final_slot].is_final = true;
@@ -401,12 +509,22 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
       sd.tracked = sd.n_in > 2;
     } else {
       for (int i = 0; i < sd.n_in; ++i) sd.in_slot[i] = ls.in_slots[i];
+      if (ls.fused_consumer) {
+        sd.kind = kGemm;
+        sd.gemm_off = (int32_t)p.gemms.size();
+        const int32_t pr = ls.gemm.fuse_pr;
+        const int64_t fsb = ls.gemm.fuse_sb, fsw = ls.gemm.fuse_sw;
+        gemm_tf32_configure(p, ls.gemm);
+        ls.gemm.fuse_pr = pr; ls.gemm.fuse_sb = fsb; ls.gemm.fuse_sw = fsw;
+        if (fsb & 3) ls.gemm.lb = 2;  // r-stride breaks 16-byte alignment of B chunks: element-wise staging
+        p.gemms.push_back(ls.gemm);
+      }
       sd.n_out_modes = (int32_t)ls.out_modes.size();
       sd.n_k_modes = (int32_t)ls.k_modes.size();
       sd.mode_off = (int32_t)p.modes.size();
       p.modes.insert(p.modes.end(), ls.out_modes.begin(), ls.out_modes.end());
       p.modes.insert(p.modes.end(), ls.k_modes.begin(), ls.k_modes.end());
-      sd.kind = (ls.tiny && allow_interp) ? kInterp : kGeneric;
+      if (!ls.fused_consumer) sd.kind = (ls.tiny && allow_interp) ? kInterp : kGeneric;
       if (sd.kind == kGeneric && allow_gemm && ls.has_gemm) {
         if (int sk = skinny_config(p, sd, ls.gemm)) {
           sd.kind = kGemm;

@@ -285,7 +285,9 @@ class Plan:
 
     @property
     def may_degenerate(self):
-        return "chain" in self.launch_kinds and not (self.flags & CTN_PLAN_EXACT_STEPS)
+        # fused chains (any dtype) and fused GEMM+consumer steps (float32) can flag a degenerate norm
+        fused = "chain" in self.launch_kinds or (self.dtype == np.float32 and "gemm" in self.launch_kinds)
+        return fused and not (self.flags & CTN_PLAN_EXACT_STEPS)
 
 
 # ---------------------------------------------------------------------------

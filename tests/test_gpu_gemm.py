@@ -175,3 +175,51 @@ def test_tf32_signed_data_normwise(gpu_engine):
     want = a.astype(np.float64) @ b.astype(np.float64)
     got = T.astype(np.float64) * np.exp(float(c))
     assert np.linalg.norm(got - want) <= 1e-5 * np.linalg.norm(want)
+
+
+# ---------------------------------------------------------------------------
+# consumer fusion (float32): GEMM + hyperedge reduce in one tcgen05 kernel
+# ---------------------------------------------------------------------------
+FUSED_CASES = [
+    ("br,prs,bp->bs", [(300, 64), (2, 64, 64), (300, 2)], ((0, 1), (0, 1)), "cfg 3 site, pr = 2"),
+    ("br,prs,bp->bs", [(200, 96), (4, 96, 64), (200, 4)], ((0, 1), (0, 1)), "pr = 4"),
+    ("prs,br,bp->bs", [(2, 40, 128), (260, 40), (260, 2)], ((0, 1), (0, 1)), "operands swapped"),
+    ("br,prs,bp->bs", [(129, 72), (2, 72, 70), (129, 2)], ((0, 1), (0, 1)), "ragged rows / columns, element-wise B staging"),
+    ("br,rps,pb->sb", [(256, 64), (64, 2, 128), (2, 256)], ((0, 1), (0, 1)), "r-major core, transposed weights and output"),
+]
+
+
+@pytest.mark.parametrize("einstr,shapes,path,what", FUSED_CASES, ids=[c[3] for c in FUSED_CASES])
+def test_fused_consumer_f32(gpu_engine, einstr, shapes, path, what):
+    rng = np.random.default_rng(hash(what) % (2 ** 32))
+    ops = [rng.uniform(0.1, 1.0, s).astype(np.float32) for s in shapes]
+    lst = planner.contract_path(einstr, *shapes, optimize=path)[1]
+    plan = gpu_engine.Plan(lst, shapes, np.float32)
+    assert plan.launch_kinds == ("gemm", "finalize"), plan.launch_kinds  # two steps, one kernel
+    T, c, fl = plan.execute_host(ops)
+    assert fl == 0
+    want_T, want_c = oracle.core_contract([o.astype(np.float64) for o in ops], lst)
+    np.testing.assert_allclose(T.astype(np.float64), want_T, rtol=1e-5, err_msg=what)
+    assert abs(float(c) - float(want_c)) < 2e-5
+    # and the unfused plan agrees
+    exact = gpu_engine.Plan(lst, shapes, np.float32, flags=gpu_engine.CTN_PLAN_EXACT_STEPS)
+    assert exact.launch_kinds == ("gemm", "generic", "finalize")
+    T2, c2, _ = exact.execute_host(ops)
+    np.testing.assert_allclose(T, T2, rtol=1e-5)
+
+
+def test_fused_consumer_degenerate_falls_back(gpu_engine):
+    """Zero weights: the reference keeps the log-scale of the GEMM step and leaves the zero
+    result unscaled; the fused kernel flags it and the engine re-runs step by step."""
+    rng = np.random.default_rng(3)
+    shapes = [(300, 64), (2, 64, 64), (300, 2)]
+    ops = [rng.uniform(0.1, 1.0, s).astype(np.float32) for s in shapes]
+    ops[2][...] = 0.0
+    lst = planner.contract_path("br,prs,bp->bs", *shapes, optimize=((0, 1), (0, 1)))[1]
+    plan = gpu_engine.Plan(lst, shapes, np.float32)
+    _, _, fl = plan.execute_host(ops)
+    assert fl & gpu_engine.CTN_RESULT_DEGENERATE
+    T, c = gpu_engine.core_contract(ops, lst)
+    want_T, want_c = oracle.core_contract(ops, lst)
+    assert np.array_equal(T, want_T)
+    assert abs(float(c) - float(want_c)) < 1e-4
