@@ -14,7 +14,10 @@ namespace ctn {
 constexpr int kMaxIn = 8;          // inputs of one generic step
 constexpr int kChainMaxIn = 512;   // inputs of one fused Hadamard-chain launch
 constexpr int kMaxPartials = 148 * 16;
-constexpr int kInterpMaxSteps = 4096;   // steps per interpreter launch (ready flags live in shared memory)  // upper bound on the grid of any reducing kernel
+constexpr int kInterpMaxSteps = 4096;   // steps per interpreter launch (ready flags live in shared memory)
+constexpr int kInterpPoolBytes = 128 * 1024;
+constexpr int kInterpRecBytes = 1024;   // one packed record per interpreter step: StepDev at 0, its modes at 256
+constexpr int kInterpRecModes = 10;     // (1024 - 256) / sizeof(ModeDev)  // shared-memory pool for the intermediates of one interpreter launch  // upper bound on the grid of any reducing kernel
 constexpr double kMinNorm = 1e-7;  // contractn/einsum.py:94
 
 // launch kinds (ctn_plan_launch_kind)
@@ -78,6 +81,8 @@ struct StepDev {
   int32_t is_final;    // output of the whole plan
   int32_t tracked;     // chain: per-element exponent tracking (n_in > 2)
   int32_t dep[kMaxIn]; // interp: launch-local index of the step producing input i (-1: ready at launch)
+  int32_t smem_out;    // interp: byte offset of this step's output in the launch's shared-memory pool (-1: none)
+  int32_t smem_in[kMaxIn];  // interp: byte offset of input i in that pool (-1: read it from global memory)
   int64_t scratch_off; // chain: byte offset of the per-tile exponent array in the arena
   int64_t out_numel;
   int64_t k_numel;
@@ -119,6 +124,8 @@ struct Launch {
   int32_t first_step, last_step;  // inclusive range of StepDev entries
   int64_t bytes;                  // algorithmic bytes moved by this launch
   double flops;
+  int32_t smem_pool = 0;          // interp: bytes of the shared-memory pool in use (0: global-memory mode)
+  int32_t rec_off = 0;            // interp: index of the launch's first packed record
 };
 
 struct Plan {
@@ -142,6 +149,8 @@ struct Plan {
   ModeDev* d_modes = nullptr;
   GemmDev* d_gemms = nullptr;
   int32_t* d_slot_list = nullptr;
+  std::vector<char> interp_recs;   // packed interpreter records (kInterpRecBytes each)
+  char* d_interp_recs = nullptr;
   int device = 0;
   int sm_count = 148;
   // host-buffer path scratch (ctn_plan_execute_host)
@@ -151,6 +160,9 @@ struct Plan {
   std::vector<size_t> h_operand_bytes;
   void* h_out = nullptr;
   double* h_log = nullptr;
+  void* h_pack = nullptr;                 // one device buffer for all small operands
+  std::vector<char> h_pack_host;          // their host-side staging image (one H2D copy)
+  std::vector<int64_t> h_pack_off;        // offset of operand i inside the pack, -1 = copied on its own
 };
 
 // kernels.cu

@@ -25,7 +25,9 @@ namespace ctn {
 
 template <typename T, bool COHERENT>
 __device__ __forceinline__ double load_elem(const T* p) {
-  if (COHERENT) return (double)__ldcg(p);  // produced earlier in this same launch
+  // COHERENT: the value may have been produced earlier in this same launch, in global OR in
+  // shared memory (interpreter): a volatile generic load is valid for both and is not cached in L1
+  if (COHERENT) return (double)*reinterpret_cast<const volatile T*>(p);
   return (double)__ldg(p);
 }
 
@@ -367,25 +369,56 @@ cudaError_t launch_finalize(const ExecCtx& c, const Launch& l) {
 // ---------------------------------------------------------------------------
 constexpr int kInterpWarps = 8;
 
+__device__ __forceinline__ void interp_fetch(unsigned char* dst, const char* src, int lane) {
+  // one 1 KB record = 64 chunks of 16 bytes: two per lane, asynchronous
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(dst + lane * 16);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(src + lane * 16) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 512), "l"(src + 512 + lane * 16) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev* __restrict__ steps,
-                                                                  const ModeDev* __restrict__ all_modes, int first,
+                                                                  const char* __restrict__ recs, int first,
                                                                   int last, DevState d, int dense,
                                                                   double* log_scale_out, int32_t* flags_out) {
-  __shared__ volatile int ready[kInterpMaxSteps];
+  extern __shared__ __align__(16) unsigned char interp_smem[];
+  // [per-warp record buffers 2 x 1 KB][ready flags: int x n_steps][pending 1/kappa: double x n_steps][pool]
+  const int n_steps = last - first + 1;
+  unsigned char* rec_buf = interp_smem;
+  unsigned char* after = interp_smem + kInterpWarps * 2 * kInterpRecBytes;
+  volatile int* ready = reinterpret_cast<volatile int*>(after);
+  volatile double* inv_s = reinterpret_cast<volatile double*>(after + ((n_steps * 4 + 15) & ~15));
+  unsigned char* pool = after + ((n_steps * 4 + 15) & ~15) + (size_t)n_steps * 8;
   __shared__ double warp_log[kInterpWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_steps = last - first + 1;
   for (int i = threadIdx.x; i < n_steps; i += blockDim.x) ready[i] = 0;
+  unsigned char* my_rec = rec_buf + warp * 2 * kInterpRecBytes;
+  if (warp < n_steps) interp_fetch(my_rec, recs + (size_t)warp * kInterpRecBytes, lane);
   __syncthreads();
   double log_acc = 0.0;  // lane 0 of each warp: sum of ln(kappa) of the steps it ran
-  for (int li = warp; li < n_steps; li += kInterpWarps) {
-    const StepDev& s = steps[first + li];
-    const ModeDev* modes = all_modes + s.mode_off;
+  int buf = 0;
+  for (int li = warp; li < n_steps; li += kInterpWarps, buf ^= 1) {
+    // descriptor + modes of this step were fetched (cp.async) while the previous one ran;
+    // start fetching the next one now
+    if (li + kInterpWarps < n_steps) {
+      interp_fetch(my_rec + (buf ^ 1) * kInterpRecBytes, recs + (size_t)(li + kInterpWarps) * kInterpRecBytes, lane);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const StepDev& s = *reinterpret_cast<const StepDev*>(my_rec + buf * kInterpRecBytes);
+    const ModeDev* modes = reinterpret_cast<const ModeDev*>(my_rec + buf * kInterpRecBytes + 256);
     const T* in[kMaxIn];
 #pragma unroll
-    for (int i = 0; i < kMaxIn; ++i) in[i] = i < s.n_in ? (const T*)d.ptrs[s.in_slot[i]] : nullptr;
+    for (int i = 0; i < kMaxIn; ++i) {
+      in[i] = nullptr;
+      if (i < s.n_in)
+        in[i] = s.smem_in[i] >= 0 ? reinterpret_cast<const T*>(pool + s.smem_in[i]) : (const T*)d.ptrs[s.in_slot[i]];
+    }
     T* out = (T*)d.ptrs[s.out_slot];
+    T* out_s = s.smem_out >= 0 ? reinterpret_cast<T*>(pool + s.smem_out) : nullptr;
     // wait for the producers of the inputs
 #pragma unroll
     for (int i = 0; i < kMaxIn; ++i)
@@ -395,27 +428,55 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
     double alpha = 1.0;
 #pragma unroll
     for (int i = 0; i < kMaxIn; ++i)
-      if (i < s.n_in) alpha *= __ldcg(&d.inv_kappa[s.in_slot[i]]);
+      if (i < s.n_in) alpha *= s.dep[i] >= 0 ? inv_s[s.dep[i]] : __ldcg(&d.inv_kappa[s.in_slot[i]]);
     const int numel = (int)s.out_numel;
     double local = 0.0;
-    for (int o = lane; o < numel; o += 32) {
-      const double v = step_element<T, true, uint32_t>(s, modes, in, (uint32_t)o);
-      const T r = (T)(v * alpha);
-      out[o] = r;
-      local += fabs((double)r);
-    }
-    const double norm = warp_sum(local);
-    if (lane == 0) {
-      // stabilize (einsum.py:89-107); the log-scale is summed per warp, merged at the end
-      const bool rescale = norm > kMinNorm;
+    if (out_s) {
+      // pooled mode: consumers inside this launch read the shared-memory copy, so publish that
+      // first and keep everything else (global copy, scale arrays, the logarithm) off the
+      // critical path of the dependency chain
+      for (int o = lane; o < numel; o += 32) {
+        const double v = step_element<T, true, uint32_t>(s, modes, in, (uint32_t)o);
+        const T r = (T)(v * alpha);
+        out_s[o] = r;
+        local += fabs((double)r);
+      }
+      const double norm = warp_sum(local);
+      const bool rescale = norm > kMinNorm;  // stabilize (einsum.py:89-107)
       const double kappa = norm / (double)s.out_numel;
-      d.kappa[s.out_slot] = rescale ? kappa : 1.0;
-      d.inv_kappa[s.out_slot] = rescale ? 1.0 / kappa : 1.0;
-      if (rescale) log_acc += log(kappa);
+      const double inv = rescale ? 1.0 / kappa : 1.0;
+      if (lane == 0) inv_s[li] = inv;
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ready[li] = 1;
+      for (int o = lane; o < numel; o += 32) out[o] = out_s[o];
+      if (lane == 0) {
+        d.kappa[s.out_slot] = rescale ? kappa : 1.0;
+        d.inv_kappa[s.out_slot] = inv;
+        if (rescale) log_acc += log(kappa);
+      }
+    } else {
+      for (int o = lane; o < numel; o += 32) {
+        const double v = step_element<T, true, uint32_t>(s, modes, in, (uint32_t)o);
+        const T r = (T)(v * alpha);
+        out[o] = r;
+        local += fabs((double)r);
+      }
+      const double norm = warp_sum(local);
+      if (lane == 0) {
+        const bool rescale = norm > kMinNorm;
+        const double kappa = norm / (double)s.out_numel;
+        const double inv = rescale ? 1.0 / kappa : 1.0;
+        d.kappa[s.out_slot] = rescale ? kappa : 1.0;
+        d.inv_kappa[s.out_slot] = inv;
+        inv_s[li] = inv;
+        if (rescale) log_acc += log(kappa);
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ready[li] = 1;
     }
-    __threadfence_block();
     __syncwarp();
-    if (lane == 0) ready[li] = 1;
   }
   if (lane == 0) warp_log[warp] = log_acc;
   __syncthreads();
@@ -440,18 +501,27 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
   }
 }
 
-cudaError_t launch_interp(const ExecCtx& c, const Launch& l) {
+template <typename T>
+static cudaError_t launch_interp_t(const ExecCtx& c, const Launch& l) {
   const Plan& p = *c.plan;
   DevState d = dev_state(c);
-  if (p.dtype == CTN_F32)
-    interp_kernel<float><<<1, kInterpWarps * 32, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
-                                                               c.out_mode == CTN_OUT_DENSE, c.log_scale_out,
-                                                               c.flags_out);
-  else
-    interp_kernel<double><<<1, kInterpWarps * 32, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, l.last_step, d,
-                                                                c.out_mode == CTN_OUT_DENSE, c.log_scale_out,
-                                                                c.flags_out);
+  const int n_steps = l.last_step - l.first_step + 1;
+  const size_t smem = (size_t)kInterpWarps * 2 * kInterpRecBytes + (((size_t)n_steps * 4 + 15) & ~(size_t)15) +
+                      (size_t)n_steps * 8 + (size_t)l.smem_pool + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(interp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  interp_kernel<T><<<1, kInterpWarps * 32, smem, c.stream>>>(p.d_steps, p.d_interp_recs + (size_t)l.rec_off * kInterpRecBytes,
+                                                            l.first_step, l.last_step, d,
+                                                            c.out_mode == CTN_OUT_DENSE, c.log_scale_out, c.flags_out);
   return cudaGetLastError();
+}
+
+cudaError_t launch_interp(const ExecCtx& c, const Launch& l) {
+  return c.plan->dtype == CTN_F32 ? launch_interp_t<float>(c, l) : launch_interp_t<double>(c, l);
 }
 
 // ---------------------------------------------------------------------------

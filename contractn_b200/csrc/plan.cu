@@ -256,7 +256,8 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
   }
   if (!ls.elementwise && n_in > kMaxIn) return CTN_ERR_UNSUPPORTED;
   double work = (double)ls.out_numel * (double)ls.k_numel * n_in;
-  ls.tiny = n_in <= kMaxIn && work <= 8192.0 && ls.out_numel <= 2048;
+  ls.tiny = n_in <= kMaxIn && work <= 8192.0 && ls.out_numel <= 2048 &&
+            ls.out_modes.size() + ls.k_modes.size() <= (size_t)kInterpRecModes;
 
   // GEMM view for pairwise steps with a summed index and no index that is
   // summed out of a single operand only
@@ -600,11 +601,11 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
       p.launches.back().bytes += bytes;
       p.launches.back().flops += ls.flops;
     } else {
-      p.launches.push_back(Launch{sd.kind, idx, idx, bytes, ls.flops});
+      p.launches.push_back(Launch{sd.kind, idx, idx, bytes, ls.flops, 0});
       if (sd.kind == kChain && sd.tracked)
-        p.launches.push_back(Launch{kMaterialize, idx, idx, 2 * out.numel * (int64_t)p.elem, 0.0});
+        p.launches.push_back(Launch{kMaterialize, idx, idx, 2 * out.numel * (int64_t)p.elem, 0.0, 0});
       if (sd.kind == kGemm && p.gemms[sd.gemm_off].splits > 1)
-        p.launches.push_back(Launch{kGemmReduce, idx, idx, (int64_t)scratch_bytes, 0.0});
+        p.launches.push_back(Launch{kGemmReduce, idx, idx, (int64_t)scratch_bytes, 0.0, 0});
     }
   }
   // the last launch must leave the canonical (T/mean|T|, log-scale) pair:
@@ -615,7 +616,38 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
   bool self_final = last.kind == kInterp || last.kind == kMaterialize;
   if (!self_final) {
     int64_t bytes = 2 * p.slots[p.final_slot].numel * (int64_t)p.elem;
-    p.launches.push_back(Launch{kFinalize, last.last_step, last.last_step, bytes, 0.0});
+    p.launches.push_back(Launch{kFinalize, last.last_step, last.last_step, bytes, 0.0, 0});
+  }
+  // Interpreter launches whose intermediates fit keep them in shared memory (every step's
+  // output gets its own place in a per-launch pool: no reuse, so the concurrently running
+  // warps cannot clobber one another); outputs are ALSO written to global memory for later launches.
+  for (auto& l : p.launches) {
+    if (l.kind != kInterp) continue;
+    size_t total = 0;
+    for (int32_t i = l.first_step; i <= l.last_step; ++i) total += align_up((size_t)p.steps[i].out_numel * p.elem, 16);
+    const bool pooled = total <= (size_t)kInterpPoolBytes;
+    size_t off = 0;
+    for (int32_t i = l.first_step; i <= l.last_step; ++i) {
+      StepDev& sdv = p.steps[i];
+      sdv.smem_out = pooled ? (int32_t)off : -1;
+      off += align_up((size_t)sdv.out_numel * p.elem, 16);
+      for (int k = 0; k < kMaxIn; ++k) {
+        sdv.smem_in[k] = -1;
+        if (pooled && k < sdv.n_in && sdv.dep[k] >= 0) sdv.smem_in[k] = p.steps[l.first_step + sdv.dep[k]].smem_out;
+      }
+    }
+    l.smem_pool = pooled ? (int32_t)std::max<size_t>(total, 16) : 0;
+    // packed records: descriptor + modes of a step in one 1 KB block the kernel fetches with cp.async
+    static_assert(sizeof(StepDev) <= 256, "StepDev must fit the record header");
+    l.rec_off = (int32_t)(p.interp_recs.size() / kInterpRecBytes);
+    for (int32_t i = l.first_step; i <= l.last_step; ++i) {
+      const StepDev& sdv = p.steps[i];
+      size_t at = p.interp_recs.size();
+      p.interp_recs.resize(at + kInterpRecBytes, 0);
+      memcpy(p.interp_recs.data() + at, &sdv, sizeof(StepDev));
+      const int nm = sdv.n_out_modes + sdv.n_k_modes;
+      if (nm > 0) memcpy(p.interp_recs.data() + at + 256, &p.modes[sdv.mode_off], (size_t)nm * sizeof(ModeDev));
+    }
   }
   p.arena_bytes = arena.top;
   layout_state(p);
@@ -650,6 +682,7 @@ static int upload_plan(Plan& p) {
   CTN_CUDA(up((void**)&p.d_modes, p.modes.data(), p.modes.size() * sizeof(ModeDev)));
   CTN_CUDA(up((void**)&p.d_gemms, p.gemms.data(), p.gemms.size() * sizeof(GemmDev)));
   CTN_CUDA(up((void**)&p.d_slot_list, p.slot_list.data(), p.slot_list.size() * sizeof(int32_t)));
+  CTN_CUDA(up((void**)&p.d_interp_recs, p.interp_recs.data(), p.interp_recs.size()));
   return CTN_OK;
 }
 
@@ -724,9 +757,11 @@ void ctn_plan_destroy(ctn_plan* plan) {
     cudaFree(p.d_modes);
     cudaFree(p.d_gemms);
     cudaFree(p.d_slot_list);
+    cudaFree(p.d_interp_recs);
     cudaFree(p.h_ws);
     cudaFree(p.h_out);
     cudaFree(p.h_log);
+    cudaFree(p.h_pack);
     std::set<void*> freed;
     for (void* q : p.h_operands)
       if (q && freed.insert(q).second) cudaFree(q);
@@ -883,8 +918,22 @@ int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void
       p.h_operand_bytes[i] = span * p.elem;
     }
   }
-  // the same host array passed for several operands (weight sharing) is
-  // uploaded once
+  // Small operands (a 1000-matrix chain has 1001 of them) are gathered on the host and go up
+  // in ONE copy; large ones are copied directly.  The same host array passed for several
+  // operands (weight sharing) is uploaded once.
+  constexpr size_t kPackLimit = 64 * 1024;
+  if (p.h_pack_off.empty()) {
+    p.h_pack_off.assign(p.n_operands, -1);
+    size_t off = 0;
+    for (int i = 0; i < p.n_operands; ++i) {
+      if (p.h_operand_bytes[i] <= kPackLimit) {
+        p.h_pack_off[i] = (int64_t)off;
+        off += align_up(std::max<size_t>(p.h_operand_bytes[i], 1), 256);
+      }
+    }
+    p.h_pack_host.assign(off, 0);
+    if (off) CTN_CUDA(cudaMalloc(&p.h_pack, off));
+  }
   std::map<const void*, int> first_use;
   std::vector<const void*> dev(p.n_operands);
   for (int i = 0; i < p.n_operands; ++i) {
@@ -894,11 +943,18 @@ int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void
       dev[i] = dev[it->second];
       continue;
     }
+    first_use[operands_host[i]] = i;
+    if (p.h_pack_off[i] >= 0) {
+      memcpy(p.h_pack_host.data() + p.h_pack_off[i], operands_host[i], p.h_operand_bytes[i]);
+      dev[i] = (const char*)p.h_pack + p.h_pack_off[i];
+      continue;
+    }
     if (!p.h_operands[i]) CTN_CUDA(cudaMalloc(&p.h_operands[i], std::max<size_t>(16, p.h_operand_bytes[i])));
     CTN_CUDA(cudaMemcpyAsync(p.h_operands[i], operands_host[i], p.h_operand_bytes[i], cudaMemcpyHostToDevice, 0));
     dev[i] = p.h_operands[i];
-    first_use[operands_host[i]] = i;
   }
+  if (!p.h_pack_host.empty())
+    CTN_CUDA(cudaMemcpyAsync(p.h_pack, p.h_pack_host.data(), p.h_pack_host.size(), cudaMemcpyHostToDevice, 0));
   int rc = ctn_plan_execute(plan, dev.data(), p.h_out, p.h_log, (int32_t*)(p.h_log + 1), p.h_ws, out_mode, nullptr);
   if (rc != CTN_OK) return rc;
   CTN_CUDA(cudaMemcpyAsync(out_host, p.h_out, (size_t)p.slots[p.final_slot].numel * p.elem, cudaMemcpyDeviceToHost, 0));
