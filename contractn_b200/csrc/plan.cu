@@ -164,6 +164,24 @@ static void fuse_gemm_group(GemmMode* g, int32_t& n, bool keep_order) {
   for (int i = 0; i < n; ++i) g[i] = fused[i];
 }
 
+// The order in which the modes of the M (or N) group are flattened into a row index is free:
+// offsets into A/B and C are computed from the same decomposition.  If the summed modes are not
+// contiguous in an operand but one of its free modes is (unit stride, even extent), make that
+// mode the innermost of its group so that tiles of the operand can be staged with 16-byte copies.
+static void prefer_unit_stride_innermost(GemmMode* grp, int n, const GemmMode* ks, int n_k, bool use_b) {
+  auto stride = [&](const GemmMode& m) { return use_b ? m.sb : m.sa; };
+  for (int i = 0; i < n_k; ++i)
+    if (stride(ks[i]) == 1) return;  // K-fast: nothing to gain
+  for (int i = 0; i + 1 < n; ++i) {
+    if (stride(grp[i]) == 1 && grp[i].extent % 4 == 0 && grp[i].extent >= 8) {
+      GemmMode m = grp[i];
+      for (int j = i; j + 1 < n; ++j) grp[j] = grp[j + 1];
+      grp[n - 1] = m;
+      return;
+    }
+  }
+}
+
 static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& live, LoweredStep& ls) {
   if (sd.n_inputs < 1 || !sd.positions || !sd.input_ranks) return CTN_ERR_INVALID;
   // pop operands exactly like `[operands.pop(x) for x in inds]` (einsum.py:344)
@@ -296,6 +314,8 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
       fuse_gemm_group(g.m, g.n_m, true);
       fuse_gemm_group(g.n, g.n_n, true);
       fuse_gemm_group(g.k, g.n_k, false);
+      prefer_unit_stride_innermost(g.m, g.n_m, g.k, g.n_k, false);
+      prefer_unit_stride_innermost(g.n, g.n_n, g.k, g.n_k, true);
       g.B = g.M = g.N = g.K = 1;
       for (int i = 0; i < g.n_batch; ++i) g.B *= g.batch[i].extent;
       for (int i = 0; i < g.n_m; ++i) g.M *= g.m[i].extent;
