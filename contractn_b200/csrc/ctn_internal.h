@@ -2,6 +2,7 @@
 // Not part of the ABI; see include/ctn_b200.h for the public surface.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -174,6 +175,11 @@ struct ExecCtx {
   double* log_scale_out;
   int32_t* flags_out;
 };
+constexpr int kInitChunk = 448;  // slot pointers carried by one init launch (kernel parameters, < 4 KB)
+struct PtrChunk {
+  void* p[kInitChunk];
+};
+cudaError_t launch_init_state(const Plan& plan, char* ws, cudaStream_t stream, const void* const* slot_ptrs);
 cudaError_t launch_generic(const ExecCtx& c, const Launch& l);
 cudaError_t launch_chain(const ExecCtx& c, const Launch& l, bool vec_ok);
 cudaError_t launch_interp(const ExecCtx& c, const Launch& l);

@@ -23,6 +23,44 @@
 
 namespace ctn {
 
+// (Re)initialise the per-execution state block: log-scale 0, flags 0, every pending scale 1,
+// arrival counters 0, and the slot -> device pointer table, which travels in the kernel
+// parameters (no host->device copy sits between two executions on a stream).
+__global__ void init_state_kernel(DevState d, int n_slots, int n_tickets, int chunk_start, int chunk_n, PtrChunk chunk) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  if (chunk_start == 0) {
+    if (t == 0) {
+      d.hdr->log_scale = 0.0;
+      d.hdr->flags = 0;
+      d.hdr->chain_exp = 0;
+      d.hdr->chain_mean = 1.0;
+      d.hdr->reserved = 0.0;
+    }
+    for (int i = t; i < n_tickets; i += stride) d.tickets[i] = 0u;
+    for (int i = t; i < n_slots; i += stride) {
+      d.inv_kappa[i] = 1.0;
+      d.kappa[i] = 1.0;
+    }
+  }
+  for (int i = t; i < chunk_n; i += stride) d.ptrs[chunk_start + i] = chunk.p[i];
+}
+
+cudaError_t launch_init_state(const Plan& p, char* ws, cudaStream_t stream, const void* const* slot_ptrs) {
+  ExecCtx c{&p, ws, stream, 0, nullptr, nullptr};
+  DevState d = dev_state(c);
+  const int n_slots = (int)p.slots.size();
+  for (int start = 0; start < n_slots; start += kInitChunk) {
+    PtrChunk chunk;
+    const int n = std::min(kInitChunk, n_slots - start);
+    for (int i = 0; i < n; ++i) chunk.p[i] = const_cast<void*>(slot_ptrs[start + i]);
+    const int grid = start == 0 ? std::max(1, std::min(64, (std::max(n_slots, p.n_tickets) + 255) / 256)) : 2;
+    init_state_kernel<<<grid, 256, 0, stream>>>(d, n_slots, p.n_tickets, start, n, chunk);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 template <typename T, bool COHERENT>
 __device__ __forceinline__ double load_elem(const T* p) {
   // COHERENT: the value may have been produced earlier in this same launch, in global OR in

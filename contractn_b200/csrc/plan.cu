@@ -840,26 +840,27 @@ static int execute_impl(const ctn_plan* plan, const void* const* operands, void*
   char* ws = (char*)workspace;
   if (((uintptr_t)ws & 255) != 0) return CTN_ERR_INVALID;
 
-  // (re)initialise the state block: log-scale 0, every pending scale 1,
-  // arrival counters 0, and the slot -> device pointer table
+  // slot -> device pointer table; the state block is (re)initialised by a small kernel
   const StateLayout& st = p.state;
-  static thread_local std::vector<char> image;
-  image.assign(st.init_bytes, 0);
-  double* inv = (double*)(image.data() + st.inv_kappa);
-  double* kap = (double*)(image.data() + st.kappa);
-  void** ptrs = (void**)(image.data() + st.ptrs);
+  static thread_local std::vector<const void*> table;
+  table.assign(p.slots.size(), nullptr);
+  const void** ptrs = table.data();
   char* arena = ws + st.total;
   for (size_t i = 0; i < p.slots.size(); ++i) {
-    inv[i] = 1.0;
-    kap[i] = 1.0;
     const Slot& s = p.slots[i];
-    if (s.operand >= 0) ptrs[i] = (void*)operands[s.operand];
+    if (s.operand >= 0) ptrs[i] = operands[s.operand];
     else if (s.is_final) ptrs[i] = out;
     else if (s.ws_offset >= 0) ptrs[i] = arena + s.ws_offset;
     else ptrs[i] = nullptr;  // fused away
     if (s.operand >= 0 && !ptrs[i]) return CTN_ERR_INVALID;
   }
-  CTN_CUDA(cudaMemcpyAsync(ws, image.data(), st.init_bytes, cudaMemcpyHostToDevice, stream));
+  {
+    cudaError_t e = launch_init_state(p, ws, stream, ptrs);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "init_state launch");
+      return CTN_ERR_CUDA;
+    }
+  }
 
   ExecCtx ctx{&p, ws, stream, out_mode, log_scale_out, flags_out};
   auto chain_vec_ok = [&](const StepDev& s) {
