@@ -656,7 +656,8 @@ static cudaError_t launch_one(const ExecCtx& c, const Launch& l, const GemmDev& 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int64_t total = g.B * ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int64_t npt = g.fuse_pr ? BN / g.fuse_pr : BN;  // output columns covered by one tile
+  const int64_t total = g.B * ((g.M + BM - 1) / BM) * ((g.N + npt - 1) / npt);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(total, p.sm_count));
   kern<<<grid, kThreadsT, SMEM_BYTES, c.stream>>>(p.d_steps, p.d_gemms, l.first_step, dev_state(c));
   return cudaGetLastError();

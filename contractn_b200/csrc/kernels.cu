@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
 #pragma unroll
     for (int i = 0; i < kMaxIn; ++i)
       if (i < s.n_in && s.dep[i] >= 0)
-        while (ready[s.dep[i]] == 0) {}
+        while (ready[s.dep[i]] == 0) __nanosleep(40);  // back off: spinning warps share issue slots with the working one
     __threadfence_block();
     double alpha = 1.0;
 #pragma unroll
