@@ -189,6 +189,170 @@ __global__ void __launch_bounds__(kSkinnyThreads) skinny_kernel(const StepDev* _
   }
 }
 
+// ---------------------------------------------------------------------------
+// float64 variant on the FP64 tensor pipe: the big operand's 8x4 DMMA fragments are loaded
+// straight from global memory (a lane reads A[row = lane/4][k = lane%4]: whole 32-byte sectors
+// when the summed index is contiguous, coalesced rows when a free index is), the small operand's
+// fragments come from shared memory, a warp owns 32 rows x NT8*8 columns of accumulators and
+// writes them as 16-byte pairs -- no shared-memory tiles, no barriers in the main loop.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void sk_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+template <int NT8, bool SWAP>
+__global__ void __launch_bounds__(kSkinnyThreads) skinny_dmma_kernel(const StepDev* __restrict__ steps,
+                                                                     const GemmDev* __restrict__ gemms, int step_idx,
+                                                                     DevState d) {
+  constexpr int NP = NT8 * 8, LDB = NP + 4;   // LDB = 4 or 12 (mod 16): conflict-free fragment reads
+  extern __shared__ double sk_smem[];          // [K_pad][LDB] small operand
+  __shared__ int64_t koff_s[kSkinnyMaxK];      // offset of summed index k in the big operand (-1: padding)
+  __shared__ int64_t ccol_s[64];
+  __shared__ double red[33];
+  __shared__ bool last_block;
+  const StepDev& s = steps[step_idx];
+  const GemmDev& g = gemms[s.gemm_off];
+  const double* big = (const double*)d.ptrs[s.in_slot[SWAP ? 1 : 0]];
+  const double* small_g = (const double*)d.ptrs[s.in_slot[SWAP ? 0 : 1]];
+  double* C = (double*)d.ptrs[s.out_slot];
+  const double alpha = d.inv_kappa[s.in_slot[0]] * d.inv_kappa[s.in_slot[1]];
+  const GemmMode* row_modes = SWAP ? g.n : g.m;
+  const GemmMode* col_modes = SWAP ? g.m : g.n;
+  const int n_row_modes = SWAP ? g.n_n : g.n_m, n_col_modes = SWAP ? g.n_m : g.n_n;
+  const int64_t R = SWAP ? g.N : g.M;
+  const int N = (int)(SWAP ? g.M : g.N);
+  const int K = (int)g.K, K_pad = (K + 3) & ~3;
+
+  for (int n = threadIdx.x; n < NP; n += blockDim.x) {
+    int64_t ox = 0, oc = 0;
+    if (n < N) sk_offsets(col_modes, n_col_modes, n, !SWAP, ox, oc);
+    ccol_s[n] = n < N ? oc : -1;
+  }
+  for (int k = threadIdx.x; k < K_pad; k += blockDim.x) {
+    int64_t ob = -1, dummy;
+    if (k < K) sk_offsets(g.k, g.n_k, k, SWAP, ob, dummy);
+    koff_s[k] = ob;
+  }
+  for (int e = threadIdx.x; e < K_pad * NP; e += blockDim.x) {
+    const int k = e / NP, n = e - k * NP;
+    double v = 0.0;
+    if (n < N && k < K) {
+      int64_t on, ok, dummy;
+      sk_offsets(col_modes, n_col_modes, n, !SWAP, on, dummy);
+      sk_offsets(g.k, g.n_k, k, !SWAP, ok, dummy);
+      v = __ldg(small_g + on + ok);
+    }
+    sk_smem[k * LDB + n] = v;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int frow = lane >> 2, fk = lane & 3;
+  const int64_t rows_per_cta = (kSkinnyThreads / 32) * 32;
+  double local_abs = 0.0;
+  for (int64_t r0 = (int64_t)blockIdx.x * rows_per_cta + warp * 32; r0 < R; r0 += (int64_t)gridDim.x * rows_per_cta) {
+    const double* arow[4];
+    int64_t crow[4];
+    bool live[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int64_t r = r0 + t * 8 + frow;
+      live[t] = r < R;
+      int64_t oa = 0, oc = 0;
+      if (live[t]) sk_offsets(row_modes, n_row_modes, r, SWAP, oa, oc);
+      arow[t] = big + oa;
+      crow[t] = oc;
+    }
+    double acc[4][NT8][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) acc[t][j][0] = acc[t][j][1] = 0.0;
+#pragma unroll 2
+    for (int ks = 0; ks < K_pad; ks += 4) {
+      const int64_t ko = koff_s[ks + fk];
+      double a[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) a[t] = (ko >= 0 && live[t]) ? __ldg(arow[t] + ko) : 0.0;
+      const double* brow = sk_smem + (ks + fk) * LDB + frow;
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) {
+        const double b = brow[j * 8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) sk_dmma(acc[t][j], a[t], b);
+      }
+    }
+    // C fragment: row = lane/4, columns 2*(lane%4) + {0, 1} of each 8x8 tile
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (!live[t]) continue;
+      double* out_row = C + crow[t];
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) {
+        const int c0 = j * 8 + fk * 2;
+        const int64_t o0 = ccol_s[c0], o1 = ccol_s[c0 + 1];
+        const double v0 = acc[t][j][0] * alpha, v1 = acc[t][j][1] * alpha;
+        if (o0 >= 0 && o1 == o0 + 1 && (((uintptr_t)(out_row + o0)) & 15) == 0) {
+          *reinterpret_cast<double2*>(out_row + o0) = make_double2(v0, v1);
+          local_abs += fabs(v0) + fabs(v1);
+        } else {
+          if (o0 >= 0) { out_row[o0] = v0; local_abs += fabs(v0); }
+          if (o1 >= 0) { out_row[o1] = v1; local_abs += fabs(v1); }
+        }
+      }
+    }
+  }
+
+  const double bsum = block_sum(local_abs, red);
+  if (threadIdx.x == 0) {
+    d.partials[blockIdx.x] = bsum;
+    __threadfence();
+    const uint32_t tk = atomicAdd(&d.tickets[s.ticket], 1u);
+    last_block = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last_block) {
+    __threadfence();
+    double a2 = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) a2 += __ldcg(&d.partials[i]);
+    const double norm = block_sum(a2, red);
+    if (threadIdx.x == 0) {
+      record_scale(d, s.out_slot, norm, s.out_numel);
+      d.tickets[s.ticket] = 0;
+    }
+  }
+}
+
+template <bool SWAP>
+static cudaError_t launch_dmma(const ExecCtx& c, const Launch& l, int64_t rows, int cols, int K) {
+  const Plan& p = *c.plan;
+  DevState d = dev_state(c);
+  const int nt8 = (cols + 7) / 8;
+  const int np = nt8 * 8, ldb = np + 4, k_pad = (K + 3) & ~3;
+  const size_t smem = (size_t)k_pad * ldb * sizeof(double);
+  const int64_t per_cta = (kSkinnyThreads / 32) * 32;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + per_cta - 1) / per_cta,
+                                                               std::min<int64_t>((int64_t)p.sm_count * 2, kMaxPartials)));
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kSkinnyThreads, smem, c.stream>>>(p.d_steps, p.d_gemms, l.first_step, d);
+    return cudaGetLastError();
+  };
+  switch (nt8) {
+    case 1: return launch(skinny_dmma_kernel<1, SWAP>);
+    case 2: return launch(skinny_dmma_kernel<2, SWAP>);
+    case 3: return launch(skinny_dmma_kernel<3, SWAP>);
+    case 4: return launch(skinny_dmma_kernel<4, SWAP>);
+    case 5: return launch(skinny_dmma_kernel<5, SWAP>);
+    case 6: return launch(skinny_dmma_kernel<6, SWAP>);
+    case 7: return launch(skinny_dmma_kernel<7, SWAP>);
+    default: return launch(skinny_dmma_kernel<8, SWAP>);
+  }
+}
+
 // column block width and rows per thread for a small side of `n` columns
 static int pick_nt(int64_t n) { return n <= 8 ? 8 : n <= 16 ? 16 : 32; }   // 33..64 columns: two blocks of 32
 static int padded_cols(int64_t n) { const int nt = pick_nt(n); return (int)((n + nt - 1) / nt) * nt; }
@@ -238,6 +402,8 @@ cudaError_t launch_skinny(const ExecCtx& c, const Launch& l) {
   const int64_t rows = swap ? g.N : g.M, cols = swap ? g.M : g.N;
   const int nt = pick_nt(cols);
   const int col_blocks = (int)((cols + nt - 1) / nt);
+  if (p.dtype == CTN_F64 && !getenv("CTN_SKINNY_NO_DMMA"))
+    return swap ? launch_dmma<true>(c, l, rows, (int)cols, (int)g.K) : launch_dmma<false>(c, l, rows, (int)cols, (int)g.K);
   if (p.dtype == CTN_F32)
     return swap ? launch_nt<float, true>(c, l, nt, rows, col_blocks) : launch_nt<float, false>(c, l, nt, rows, col_blocks);
   return swap ? launch_nt<double, true>(c, l, nt, rows, col_blocks) : launch_nt<double, false>(c, l, nt, rows, col_blocks);
