@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kSkinnyThreads) skinny_dmma_kernel(const StepD
     for (int t = 0; t < 4; ++t)
 #pragma unroll
       for (int j = 0; j < NT8; ++j) acc[t][j][0] = acc[t][j][1] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int ks = 0; ks < K_pad; ks += 4) {
       const int64_t ko = koff_s[ks + fk];
       double a[4];
