@@ -1,0 +1,41 @@
+"""Correctness of batch sharding across GPUs: every rank contracts its shard of a batched hub,
+the shards are merged to the global scale, and rank 0 compares with the unsharded contraction.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29540 benchmarks/check_batch_shards.py"""
+import json, os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from contractn_b200 import engine, parallel, planner
+
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+out = {}
+for dtype in (np.float64, np.float32):
+    rng = np.random.default_rng(7)
+    n, B = 24, 4096 * world
+    full = [rng.uniform(0.5, 1.5, (3, B)).astype(dtype) for _ in range(n)]
+    for o in full[:3]:
+        o[:, B // 2:] *= 1e-3          # shards with very different magnitudes
+    einstr = ",".join(["ab"] * n) + "->ab"
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    mine = [torch.as_tensor(np.ascontiguousarray(o[:, lo:hi])).to(dev) for o in full]
+    lst = planner.contract_path(einstr, *[tuple(t.shape) for t in mine])[1]
+    T, c = engine.core_contract(mine, lst)
+    T, c = parallel.merge_batch_shards(T, c)
+    lst_full = planner.contract_path(einstr, *[o.shape for o in full])[1]
+    Tf, cf = engine.core_contract([torch.as_tensor(o).to(dev) for o in full], lst_full)
+    err_T = float((T.double() - Tf[:, lo:hi].double()).abs().max() / Tf.double().abs().max())
+    err_c = abs(float(c[0]) - float(cf))
+    res = torch.tensor([err_T, err_c], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    out[np.dtype(dtype).name] = {"max_rel_err_T": float(res[0]), "abs_err_log_scale": float(res[1])}
+if rank == 0:
+    print(json.dumps({"world": world, **out}))
+    assert out["float64"]["max_rel_err_T"] < 1e-12 and out["float64"]["abs_err_log_scale"] < 1e-9
+    assert out["float32"]["max_rel_err_T"] < 1e-5
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()

@@ -180,6 +180,8 @@ struct PtrChunk {
   void* p[kInitChunk];
 };
 cudaError_t launch_init_state(const Plan& plan, char* ws, cudaStream_t stream, const void* const* slot_ptrs);
+cudaError_t launch_merge_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
+                                double* log_scale_out, cudaStream_t stream);
 cudaError_t launch_generic(const ExecCtx& c, const Launch& l);
 cudaError_t launch_chain(const ExecCtx& c, const Launch& l, bool vec_ok);
 cudaError_t launch_interp(const ExecCtx& c, const Launch& l);

@@ -563,6 +563,37 @@ cudaError_t launch_interp(const ExecCtx& c, const Launch& l) {
 }
 
 // ---------------------------------------------------------------------------
+// multi-GPU: rescale a batch shard to the global scale (one launch, scalars recomputed per thread)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) merge_shards_kernel(T* data, int64_t numel, const double* __restrict__ table,
+                                                                int world, int rank, double* log_scale_out) {
+  double c_star = -INFINITY;
+  for (int i = 0; i < world; ++i) c_star = fmax(c_star, table[3 * i]);
+  double S = 0.0, N = 0.0;
+  for (int i = 0; i < world; ++i) {  // fixed order: every rank computes the same bits
+    S += table[3 * i + 1] * exp(table[3 * i] - c_star);
+    N += table[3 * i + 2];
+  }
+  const double kappa = S / N;
+  const double scale = exp(table[3 * rank] - c_star) / kappa;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    data[i] = (T)((double)data[i] * scale);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *log_scale_out = c_star + log(kappa);
+}
+
+cudaError_t launch_merge_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
+                                double* log_scale_out, cudaStream_t stream) {
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((numel + kThreads - 1) / kThreads, 148 * 8));
+  if (dtype == CTN_F32)
+    merge_shards_kernel<float><<<grid, kThreads, 0, stream>>>((float*)data, numel, table, world, rank, log_scale_out);
+  else
+    merge_shards_kernel<double><<<grid, kThreads, 0, stream>>>((double*)data, numel, table, world, rank, log_scale_out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Hadamard chain
 // ---------------------------------------------------------------------------
 template <typename T, bool VEC>

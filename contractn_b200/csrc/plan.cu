@@ -918,6 +918,18 @@ int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, vo
   return rc;
 }
 
+int ctn_merge_batch_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
+                           double* log_scale_out, void* stream) {
+  if (!data || !table || !log_scale_out || world < 1 || rank < 0 || rank >= world || numel < 0) return CTN_ERR_INVALID;
+  if (dtype != CTN_F32 && dtype != CTN_F64) return CTN_ERR_UNSUPPORTED;
+  cudaError_t e = launch_merge_shards(data, numel, dtype, table, world, rank, log_scale_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "merge_shards launch");
+    return CTN_ERR_CUDA;
+  }
+  return CTN_OK;
+}
+
 int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void* out_host,
                           double* log_scale_host, int32_t* flags_host, int out_mode) {
   if (!plan || !operands_host || !out_host || !log_scale_host) return CTN_ERR_INVALID;

@@ -52,6 +52,20 @@ def merge_batch_shards(T_local, c_local, group=None):
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)  # (gloo has no all_gather_into_tensor)
     table = torch.stack(parts)
+    if T_local.is_cuda and T_local.is_contiguous() and T_local.dtype in (torch.float32, torch.float64):
+        # one kernel of the engine does the scalar algebra and the in-place rescale
+        from . import engine
+
+        lib = engine.load_library()
+        c_out = torch.empty(1, dtype=torch.float64, device=T_local.device)
+        rank = dist.get_rank(group)
+        engine._check(
+            lib.ctn_merge_batch_shards(T_local.data_ptr(), T_local.numel(),
+                                       engine.CTN_F32 if T_local.dtype == torch.float32 else engine.CTN_F64,
+                                       table.data_ptr(), world, rank, c_out.data_ptr(),
+                                       torch.cuda.current_stream(T_local.device).cuda_stream),
+            "ctn_merge_batch_shards")
+        return T_local, c_out
     c_star = table[:, 0].max()
     w_all = torch.exp(table[:, 0] - c_star)
     kappa = (table[:, 1] * w_all).sum() / table[:, 2].sum()

@@ -156,6 +156,15 @@ int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, vo
 int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void* out_host,
                           double* log_scale_host, int32_t* flags_host, int out_mode);
 
+/* Batch-sharded evaluations (one process per GPU): bring this rank's shard of the split-format
+ * result to the GLOBAL scale.  `table` is the all-gathered [world][3] array of
+ * (log-scale, sum|T_shard|, numel_shard) per rank (device memory); the kernel rescales `data` in
+ * place by exp(c_rank - c*) / kappa and writes the common log-scale c* + ln(kappa) to *log_scale_out,
+ * where c* = max_i c_i and kappa = sum_i(abs_i * exp(c_i - c*)) / sum_i numel_i -- the reference's
+ * single global scale for the unsharded tensor (contractn/einsum.py:89-107). */
+int ctn_merge_batch_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
+                           double* log_scale_out, void* stream);
+
 const char* ctn_status_string(int status);
 const char* ctn_last_cuda_error(void);
 int ctn_abi_version(void);
