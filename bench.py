@@ -13,7 +13,7 @@ resident in HBM; ``e2e`` = the same through the public API
 (``TN.make_contract_fun`` -> ``contract`` -> ``ctn_plan_execute_host``) with
 pinned HOST buffers, H2D/D2H inside the timed region.  N > 1: one process per
 GPU, the batch is sharded (weak scaling: B evaluations per GPU), the shards'
-(mantissa, log-scale) pairs are merged with two scalar NCCL all-reduces.
+(mantissa, log-scale) pairs are merged to one global scale after a 24-byte NCCL all-gather.
 """
 import argparse
 import json

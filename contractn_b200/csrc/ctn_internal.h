@@ -180,6 +180,9 @@ struct PtrChunk {
   void* p[kInitChunk];
 };
 cudaError_t launch_init_state(const Plan& plan, char* ws, cudaStream_t stream, const void* const* slot_ptrs);
+constexpr int kShardStatBlocks = 148;  // CTN_SHARD_STATS_WORDS = 3 + kShardStatBlocks + 1 doubles
+cudaError_t launch_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws,
+                               cudaStream_t stream);
 cudaError_t launch_merge_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                                 double* log_scale_out, cudaStream_t stream);
 cudaError_t launch_generic(const ExecCtx& c, const Launch& l);

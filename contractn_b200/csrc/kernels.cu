@@ -583,6 +583,47 @@ __global__ void __launch_bounds__(kThreads) merge_shards_kernel(T* data, int64_t
   if (blockIdx.x == 0 && threadIdx.x == 0) *log_scale_out = c_star + log(kappa);
 }
 
+// (log-scale, sum|T|, numel) of one shard in ONE launch: per-block partials in ws[3..3+grid), the last block
+// (ticket in ws[kShardStatBlocks+3], left at zero again) adds them in block order -> same bits every run.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) shard_stats_kernel(const T* __restrict__ data, int64_t numel,
+                                                               const double* __restrict__ log_scale, double* ws) {
+  double s = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) s += fabs((double)data[i]);
+  __shared__ double red[33];
+  __shared__ bool last;
+  s = block_sum(s, red);
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws + 3 + kShardStatBlocks);
+  if (threadIdx.x == 0) {
+    ws[3 + blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) tot += ((volatile double*)ws)[3 + b];
+    ws[0] = *log_scale;
+    ws[1] = tot;
+    ws[2] = (double)numel;
+    *ticket = 0u;
+  }
+}
+
+cudaError_t launch_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws,
+                               cudaStream_t stream) {
+  const int grid =
+      (int)std::max<int64_t>(1, std::min<int64_t>((numel + kThreads * 8 - 1) / (kThreads * 8), kShardStatBlocks));
+  if (dtype == CTN_F32)
+    shard_stats_kernel<float><<<grid, kThreads, 0, stream>>>((const float*)data, numel, log_scale, ws);
+  else
+    shard_stats_kernel<double><<<grid, kThreads, 0, stream>>>((const double*)data, numel, log_scale, ws);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                                 double* log_scale_out, cudaStream_t stream) {
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((numel + kThreads - 1) / kThreads, 148 * 8));

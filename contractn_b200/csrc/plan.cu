@@ -918,6 +918,18 @@ int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, vo
   return rc;
 }
 
+int ctn_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws, void* stream) {
+  static_assert(CTN_SHARD_STATS_WORDS == 3 + kShardStatBlocks + 1, "header constant out of date");
+  if (!data || !log_scale || !ws || numel < 0) return CTN_ERR_INVALID;
+  if (dtype != CTN_F32 && dtype != CTN_F64) return CTN_ERR_UNSUPPORTED;
+  cudaError_t e = launch_shard_stats(data, numel, dtype, log_scale, ws, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "shard_stats launch");
+    return CTN_ERR_CUDA;
+  }
+  return CTN_OK;
+}
+
 int ctn_merge_batch_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                            double* log_scale_out, void* stream) {
   if (!data || !table || !log_scale_out || world < 1 || rank < 0 || rank >= world || numel < 0) return CTN_ERR_INVALID;

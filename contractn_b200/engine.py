@@ -41,8 +41,11 @@ EXPORTS = (
     "ctn_plan_output_rank", "ctn_plan_output_extents", "ctn_plan_output_numel",
     "ctn_plan_num_launches", "ctn_plan_flops", "ctn_plan_step_bytes",
     "ctn_plan_launch_kind", "ctn_plan_execute", "ctn_plan_execute_timed", "ctn_plan_execute_host",
-    "ctn_merge_batch_shards", "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
+    "ctn_shard_stats", "ctn_merge_batch_shards", "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
 )
+
+
+CTN_SHARD_STATS_WORDS = 152  # include/ctn_b200.h
 
 
 class EngineError(RuntimeError):
@@ -118,6 +121,8 @@ def load_library():
         lib.ctn_plan_execute_host.argtypes = [vp, ctypes.POINTER(vp), vp, ctypes.POINTER(dbl),
                                               ctypes.POINTER(i32), ctypes.c_int]
         lib.ctn_plan_execute_host.restype = ctypes.c_int
+        lib.ctn_shard_stats.argtypes = [vp, i64, ctypes.c_int, vp, vp, vp]
+        lib.ctn_shard_stats.restype = ctypes.c_int
         lib.ctn_merge_batch_shards.argtypes = [vp, i64, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, vp]
         lib.ctn_merge_batch_shards.restype = ctypes.c_int
         lib.ctn_status_string.argtypes = [ctypes.c_int]

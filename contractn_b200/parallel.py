@@ -6,8 +6,9 @@ path shards naturally:
 * **batch sharding** -- independent network evaluations along a batch hub are
   split across ranks; each rank contracts its shard to a split-format pair
   ``(T_r, c_r)`` with its OWN scale, and :func:`merge_batch_shards` restores the
-  reference's single global scale with two scalar all-reduces (the output
-  stays sharded).
+  reference's single global scale after one 24-byte-per-rank all-gather (the
+  output stays sharded; on CUDA the scalar algebra and the rescale are two
+  kernels of the engine, ``ctn_shard_stats`` and ``ctn_merge_batch_shards``).
 * **bond slicing** -- the largest contracted bonds are fixed to one value per
   slice, slices are distributed round-robin, every rank accumulates its slices
   with a log-sum-exp merge and :func:`merge_slice_sums` all-reduces the
@@ -30,6 +31,20 @@ def _world(group=None):
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
+_SHARD_BUFFERS = {}
+
+
+def _shard_buffers(dev, world):
+    """Per-device scratch of the CUDA merge (reused in stream order; the stats ticket must start at zero)."""
+    key = (dev.index, world)
+    if key not in _SHARD_BUFFERS:
+        from .engine import CTN_SHARD_STATS_WORDS
+
+        _SHARD_BUFFERS[key] = (torch.zeros(CTN_SHARD_STATS_WORDS, dtype=torch.float64, device=dev),
+                               torch.empty(world * 3, dtype=torch.float64, device=dev))
+    return _SHARD_BUFFERS[key]
+
+
 def merge_batch_shards(T_local, c_local, group=None):
     """Global split-format pair for a batch-sharded evaluation.
 
@@ -40,10 +55,28 @@ def merge_batch_shards(T_local, c_local, group=None):
     returns for the unsharded network.  One small all-gather (3 doubles per
     rank) is the only communication.
     """
-    c_local = c_local.reshape(-1)[0].to(torch.float64)
     if _world(group) == 1:
-        return T_local, c_local.reshape(1)
+        return T_local, c_local.reshape(-1)[:1].to(torch.float64)
     world = _world(group)
+    if T_local.is_cuda and T_local.is_contiguous() and T_local.dtype in (torch.float32, torch.float64) \
+            and c_local.dtype == torch.float64:
+        # three launches in all: stats kernel -> NCCL all-gather of 24 B per rank -> merge kernel
+        from . import engine
+
+        lib = engine.load_library()
+        dev = T_local.device
+        ws, table = _shard_buffers(dev, world)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        dt = engine.CTN_F32 if T_local.dtype == torch.float32 else engine.CTN_F64
+        engine._check(lib.ctn_shard_stats(T_local.data_ptr(), T_local.numel(), dt, c_local.data_ptr(),
+                                          ws.data_ptr(), stream), "ctn_shard_stats")
+        dist.all_gather_into_tensor(table, ws[:3], group=group)
+        c_out = torch.empty(1, dtype=torch.float64, device=dev)
+        engine._check(lib.ctn_merge_batch_shards(T_local.data_ptr(), T_local.numel(), dt, table.data_ptr(), world,
+                                                 dist.get_rank(group), c_out.data_ptr(), stream),
+                      "ctn_merge_batch_shards")
+        return T_local, c_out
+    c_local = c_local.reshape(-1)[0].to(torch.float64)
     # sum|T_local| is numel when the shard was rescaled by its last step, but a
     # shard whose norms fall under the reference's 1e-7 threshold is returned
     # unscaled (contractn/einsum.py:102), so measure it (one reduction pass)
@@ -52,20 +85,6 @@ def merge_batch_shards(T_local, c_local, group=None):
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)  # (gloo has no all_gather_into_tensor)
     table = torch.stack(parts)
-    if T_local.is_cuda and T_local.is_contiguous() and T_local.dtype in (torch.float32, torch.float64):
-        # one kernel of the engine does the scalar algebra and the in-place rescale
-        from . import engine
-
-        lib = engine.load_library()
-        c_out = torch.empty(1, dtype=torch.float64, device=T_local.device)
-        rank = dist.get_rank(group)
-        engine._check(
-            lib.ctn_merge_batch_shards(T_local.data_ptr(), T_local.numel(),
-                                       engine.CTN_F32 if T_local.dtype == torch.float32 else engine.CTN_F64,
-                                       table.data_ptr(), world, rank, c_out.data_ptr(),
-                                       torch.cuda.current_stream(T_local.device).cuda_stream),
-            "ctn_merge_batch_shards")
-        return T_local, c_out
     c_star = table[:, 0].max()
     w_all = torch.exp(table[:, 0] - c_star)
     kappa = (table[:, 1] * w_all).sum() / table[:, 2].sum()

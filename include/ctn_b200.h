@@ -156,7 +156,15 @@ int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, vo
 int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void* out_host,
                           double* log_scale_host, int32_t* flags_host, int out_mode);
 
-/* Batch-sharded evaluations (one process per GPU): bring this rank's shard of the split-format
+/* Batch-sharded evaluations, step 1: this rank's (log-scale, sum|T_shard|, numel_shard) triple in one
+ * kernel.  `ws` is CTN_SHARD_STATS_WORDS doubles of device memory, ZERO before the first use (the
+ * kernel leaves its ticket word at zero again); ws[0..2] is the triple to all-gather, the rest is
+ * scratch.  sum|T| is measured, not assumed = numel: a shard under the reference's 1e-7 threshold
+ * is returned unscaled (contractn/einsum.py:102). */
+#define CTN_SHARD_STATS_WORDS 152
+int ctn_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws, void* stream);
+
+/* Batch-sharded evaluations, step 2 (one process per GPU): bring this rank's shard of the split-format
  * result to the GLOBAL scale.  `table` is the all-gathered [world][3] array of
  * (log-scale, sum|T_shard|, numel_shard) per rank (device memory); the kernel rescales `data` in
  * place by exp(c_rank - c*) / kappa and writes the common log-scale c* + ln(kappa) to *log_scale_out,
