@@ -80,8 +80,8 @@ struct StepDev {
   int32_t gemm_off;    // index into the plan's GemmDev table (-1 = none)
   int32_t ticket;      // index of this step's arrival counter
   int32_t is_final;    // output of the whole plan
-  int32_t tracked;     // chain: per-element exponent tracking (n_in > 2)
-  int32_t dep[kMaxIn]; // interp: launch-local index of the step producing input i (-1: ready at launch)
+  int32_t tracked;     // chain: per-element exponent tracking (n_in > 2); interp: pairwise 32-bit short path
+  int32_t dep[kMaxIn]; // interp: launch-local index of the step producing input i (-1: ready at launch)  (-1: made by an earlier launch, -2: operand)
   int32_t smem_out;    // interp: byte offset of this step's output in the launch's shared-memory pool (-1: none)
   int32_t smem_in[kMaxIn];  // interp: byte offset of input i in that pool (-1: read it from global memory)
   int64_t scratch_off; // chain: byte offset of the per-tile exponent array in the arena
@@ -120,6 +120,13 @@ struct Slot {
   bool is_final = false;
 };
 
+struct InterpPreload {
+  int32_t slot;      // source tensor (operand or earlier intermediate)
+  int32_t pool_off;  // byte offset in the launch's pool
+  int32_t n_elems;   // address span in elements (1 + sum (extent-1)*stride): strided views keep their strides
+  int32_t pad;
+};
+
 struct Launch {
   int32_t kind;
   int32_t first_step, last_step;  // inclusive range of StepDev entries
@@ -127,6 +134,7 @@ struct Launch {
   double flops;
   int32_t smem_pool = 0;          // interp: bytes of the shared-memory pool in use (0: global-memory mode)
   int32_t rec_off = 0;            // interp: index of the launch's first packed record
+  int32_t pre_off = 0, pre_n = 0; // interp: inputs from outside the launch staged into the shared-memory pool
 };
 
 struct Plan {
@@ -152,6 +160,8 @@ struct Plan {
   int32_t* d_slot_list = nullptr;
   std::vector<char> interp_recs;   // packed interpreter records (kInterpRecBytes each)
   char* d_interp_recs = nullptr;
+  std::vector<InterpPreload> interp_pre;  // per interpreter launch: external inputs copied to the pool at kernel start
+  InterpPreload* d_interp_pre = nullptr;
   int device = 0;
   int sm_count = 148;
   // host-buffer path scratch (ctn_plan_execute_host)

@@ -125,6 +125,52 @@ __device__ __forceinline__ double step_element(const StepDev& s, const ModeDev* 
   return acc;
 }
 
+// One output element of a PAIRWISE step with 32-bit offsets (interpreter short path: the generic
+// routine above spends ~3000 cycles per 3x3 product on predicated 8-operand 64-bit index algebra).
+template <typename T>
+__device__ __forceinline__ double pair_element(const StepDev& s, const ModeDev* __restrict__ modes, const T* a,
+                                               const T* b, uint32_t o) {
+  uint32_t oa = 0, ob = 0, rem = o;
+  for (int m = s.n_out_modes - 1; m > 0; --m) {
+    const ModeDev& md = modes[m];
+    const uint32_t e = (uint32_t)md.extent;
+    const uint32_t q = rem / e, idx = rem - q * e;
+    rem = q;
+    oa += idx * (uint32_t)md.stride[0];
+    ob += idx * (uint32_t)md.stride[1];
+  }
+  if (s.n_out_modes > 0) {
+    oa += rem * (uint32_t)modes[0].stride[0];
+    ob += rem * (uint32_t)modes[0].stride[1];
+  }
+  if (s.n_k_modes == 0) return load_elem<T, true>(a + oa) * load_elem<T, true>(b + ob);
+  if (s.k_numel == 0) return 0.0;
+  const ModeDev* km = modes + s.n_out_modes;
+  const int nk = s.n_k_modes;
+  const uint32_t inner_n = (uint32_t)km[nk - 1].extent;
+  const uint32_t isa = (uint32_t)km[nk - 1].stride[0], isb = (uint32_t)km[nk - 1].stride[1];
+  const uint32_t outer_n = (uint32_t)s.k_numel / inner_n;
+  double acc = 0.0;
+  for (uint32_t ko = 0; ko < outer_n; ++ko) {
+    uint32_t pa = oa, pb = ob, r = ko;
+    for (int m = nk - 2; m >= 0; --m) {
+      const uint32_t e = (uint32_t)km[m].extent;
+      const uint32_t q = r / e, idx = r - q * e;
+      r = q;
+      pa += idx * (uint32_t)km[m].stride[0];
+      pb += idx * (uint32_t)km[m].stride[1];
+    }
+    for (uint32_t kk = 0; kk < inner_n; ++kk) {
+      double pr = load_elem<T, true>(a + pa);
+      pr *= load_elem<T, true>(b + pb);
+      acc += pr;
+      pa += isa;
+      pb += isb;
+    }
+  }
+  return acc;
+}
+
 // ---------------------------------------------------------------------------
 // generic step kernel
 // ---------------------------------------------------------------------------
@@ -406,6 +452,18 @@ cudaError_t launch_finalize(const ExecCtx& c, const Launch& l) {
 // costs one L2 round trip per step instead of a kernel launch.
 // ---------------------------------------------------------------------------
 constexpr int kInterpWarps = 8;
+#ifndef CTN_INTERP_BACKOFF
+#define CTN_INTERP_BACKOFF do {} while (0)
+#endif
+#ifdef CTN_INTERP_PROFILE
+__device__ long long g_interp_prof[4096 * 8];
+extern "C" int ctn_debug_interp_profile(long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_interp_prof, (size_t)n * 8 * sizeof(long long));
+}
+#define PROF(k) do { if (lane == 0 && li < 4096) g_interp_prof[li * 8 + (k)] = clock64(); } while (0)
+#else
+#define PROF(k) do {} while (0)
+#endif
 
 __device__ __forceinline__ void interp_fetch(unsigned char* dst, const char* src, int lane) {
   // one 1 KB record = 64 chunks of 16 bytes: two per lane, asynchronous
@@ -417,8 +475,9 @@ __device__ __forceinline__ void interp_fetch(unsigned char* dst, const char* src
 
 template <typename T>
 __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev* __restrict__ steps,
-                                                                  const char* __restrict__ recs, int first,
-                                                                  int last, DevState d, int dense,
+                                                                  const char* __restrict__ recs,
+                                                                  const InterpPreload* __restrict__ pre, int n_pre,
+                                                                  int first, int last, DevState d, int dense,
                                                                   double* log_scale_out, int32_t* flags_out) {
   extern __shared__ __align__(16) unsigned char interp_smem[];
   // [per-warp record buffers 2 x 1 KB][ready flags: int x n_steps][pending 1/kappa: double x n_steps][pool]
@@ -433,6 +492,14 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
   for (int i = threadIdx.x; i < n_steps; i += blockDim.x) ready[i] = 0;
   unsigned char* my_rec = rec_buf + warp * 2 * kInterpRecBytes;
   if (warp < n_steps) interp_fetch(my_rec, recs + (size_t)warp * kInterpRecBytes, lane);
+  // stage the launch's external inputs (one thread per tensor: independent loads, all in flight together)
+  for (int e = threadIdx.x; e < n_pre; e += blockDim.x) {
+    const InterpPreload q = pre[e];
+    const T* src = (const T*)d.ptrs[q.slot];
+    T* dst = reinterpret_cast<T*>(pool + q.pool_off);
+#pragma unroll 4
+    for (int i = 0; i < q.n_elems; ++i) dst[i] = __ldcg(src + i);
+  }
   __syncthreads();
   double log_acc = 0.0;  // lane 0 of each warp: sum of ln(kappa) of the steps it ran
   int buf = 0;
@@ -457,39 +524,131 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
     }
     T* out = (T*)d.ptrs[s.out_slot];
     T* out_s = s.smem_out >= 0 ? reinterpret_cast<T*>(pool + s.smem_out) : nullptr;
-    // wait for the producers of the inputs
-#pragma unroll
-    for (int i = 0; i < kMaxIn; ++i)
-      if (i < s.n_in && s.dep[i] >= 0)
-        while (ready[s.dep[i]] == 0) __nanosleep(40);  // back off: spinning warps share issue slots with the working one
-    __threadfence_block();
-    double alpha = 1.0;
-#pragma unroll
-    for (int i = 0; i < kMaxIn; ++i)
-      if (i < s.n_in) alpha *= s.dep[i] >= 0 ? inv_s[s.dep[i]] : __ldcg(&d.inv_kappa[s.in_slot[i]]);
+    PROF(0);
     const int numel = (int)s.out_numel;
+    // Short path (pairwise, <= 32 outputs, at most one summed mode): one output per lane, and ALL of
+    // its index algebra happens here, before the wait -- after it only loads and an FMA chain remain.
+    const bool quick = out_s != nullptr && s.tracked && numel <= 32 && s.n_k_modes <= 1;
+    uint32_t qa = 0, qb = 0, qsa = 0, qsb = 0, qn = 0;
+    if (quick && lane < numel) {
+      uint32_t rem = (uint32_t)lane;
+      for (int m = s.n_out_modes - 1; m > 0; --m) {
+        const uint32_t e = (uint32_t)modes[m].extent;
+        const uint32_t q = rem / e, idx = rem - q * e;
+        rem = q;
+        qa += idx * (uint32_t)modes[m].stride[0];
+        qb += idx * (uint32_t)modes[m].stride[1];
+      }
+      if (s.n_out_modes > 0) {
+        qa += rem * (uint32_t)modes[0].stride[0];
+        qb += rem * (uint32_t)modes[0].stride[1];
+      }
+      qn = 1;
+      if (s.n_k_modes == 1) {
+        const ModeDev& km = modes[s.n_out_modes];
+        qn = (uint32_t)km.extent;
+        qsa = (uint32_t)km.stride[0];
+        qsb = (uint32_t)km.stride[1];
+      }
+    }
+    // pending scales of inputs made by earlier launches: loaded before the wait, off the dependency chain
+    // (the first two inputs are handled in registers: an 8-way predicated loop over the record costs
+    // ~35 cycles per slot on the critical path)
+    const int n_in = s.n_in;
+    const int dep0 = s.dep[0], dep1 = n_in > 1 ? s.dep[1] : -2;
+    const double numel_d = (double)s.out_numel;
+    double alpha = 1.0;
+    if (dep0 == -1) alpha *= __ldcg(&d.inv_kappa[s.in_slot[0]]);
+    if (dep1 == -1) alpha *= __ldcg(&d.inv_kappa[s.in_slot[1]]);
+    if (n_in > 2) {
+#pragma unroll 1
+      for (int i = 2; i < n_in; ++i)
+        if (s.dep[i] == -1) alpha *= __ldcg(&d.inv_kappa[s.in_slot[i]]);
+    }
+    // wait for the producers of the inputs
+    if (dep0 >= 0)
+      while (ready[dep0] == 0) CTN_INTERP_BACKOFF;
+    if (dep1 >= 0)
+      while (ready[dep1] == 0) CTN_INTERP_BACKOFF;
+    if (n_in > 2) {
+#pragma unroll 1
+      for (int i = 2; i < n_in; ++i)
+        if (s.dep[i] >= 0)
+          while (ready[s.dep[i]] == 0) CTN_INTERP_BACKOFF;
+    }
+    PROF(1);
+    // pooled mode: everything made inside the launch is read from shared memory, written by a warp of
+    // this CTA before its (volatile) ready flag -- a compiler barrier is enough on the reading side
+    if (out_s) asm volatile("" ::: "memory");
+    else __threadfence_block();
+    if (dep0 >= 0) alpha *= inv_s[dep0];
+    if (dep1 >= 0) alpha *= inv_s[dep1];
+    if (n_in > 2) {
+#pragma unroll 1
+      for (int i = 2; i < n_in; ++i)
+        if (s.dep[i] >= 0) alpha *= inv_s[s.dep[i]];
+    }
+    PROF(4);
     double local = 0.0;
     if (out_s) {
       // pooled mode: consumers inside this launch read the shared-memory copy, so publish that
       // first and keep everything else (global copy, scale arrays, the logarithm) off the
       // critical path of the dependency chain
-      for (int o = lane; o < numel; o += 32) {
-        const double v = step_element<T, true, uint32_t>(s, modes, in, (uint32_t)o);
-        const T r = (T)(v * alpha);
-        out_s[o] = r;
-        local += fabs((double)r);
+      if (quick) {
+        const T* a = in[0] + qa;
+        const T* b = in[1] + qb;
+        double acc = 0.0;
+        uint32_t kk = 0;
+        for (; kk + 4 <= qn; kk += 4) {
+          const double a0 = (double)a[kk * qsa], a1 = (double)a[(kk + 1) * qsa], a2 = (double)a[(kk + 2) * qsa],
+                       a3 = (double)a[(kk + 3) * qsa];
+          const double b0 = (double)b[kk * qsb], b1 = (double)b[(kk + 1) * qsb], b2 = (double)b[(kk + 2) * qsb],
+                       b3 = (double)b[(kk + 3) * qsb];
+          acc = fma(a0, b0, acc); acc = fma(a1, b1, acc); acc = fma(a2, b2, acc); acc = fma(a3, b3, acc);
+        }
+        {  // tail of up to three terms: all loads first, then the FMA chain (x + 0*0 == x)
+          const uint32_t r = qn - kk;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+          if (r > 0) { a0 = (double)a[kk * qsa]; b0 = (double)b[kk * qsb]; }
+          if (r > 1) { a1 = (double)a[(kk + 1) * qsa]; b1 = (double)b[(kk + 1) * qsb]; }
+          if (r > 2) { a2 = (double)a[(kk + 2) * qsa]; b2 = (double)b[(kk + 2) * qsb]; }
+          acc = fma(a0, b0, acc); acc = fma(a1, b1, acc); acc = fma(a2, b2, acc);
+        }
+        if (lane < numel) {
+          const T r = (T)(acc * alpha);
+          out_s[lane] = r;
+          local = fabs((double)r);
+        }
+      } else if (s.tracked) {
+        for (int o = lane; o < numel; o += 32) {
+          const T r = (T)(pair_element<T>(s, modes, in[0], in[1], (uint32_t)o) * alpha);
+          out_s[o] = r;
+          local += fabs((double)r);
+        }
+      } else {
+        for (int o = lane; o < numel; o += 32) {
+          const double v = step_element<T, true, uint32_t>(s, modes, in, (uint32_t)o);
+          const T r = (T)(v * alpha);
+          out_s[o] = r;
+          local += fabs((double)r);
+        }
       }
+      PROF(2);
       const double norm = warp_sum(local);
+      PROF(5);
       const bool rescale = norm > kMinNorm;  // stabilize (einsum.py:89-107)
-      const double kappa = norm / (double)s.out_numel;
-      const double inv = rescale ? 1.0 / kappa : 1.0;
+      // ONE division on the critical path: the applied factor is numel/norm; kappa and the log-scale
+      // are derived from that same factor afterwards, so the pair stays exactly consistent
+      const double inv = rescale ? numel_d / norm : 1.0;
       if (lane == 0) inv_s[li] = inv;
       __threadfence_block();
       __syncwarp();
       if (lane == 0) ready[li] = 1;
+      PROF(3);
       for (int o = lane; o < numel; o += 32) out[o] = out_s[o];
       if (lane == 0) {
-        d.kappa[s.out_slot] = rescale ? kappa : 1.0;
+        const double kappa = rescale ? 1.0 / inv : 1.0;
+        d.kappa[s.out_slot] = kappa;
         d.inv_kappa[s.out_slot] = inv;
         if (rescale) log_acc += log(kappa);
       }
@@ -553,7 +712,7 @@ static cudaError_t launch_interp_t(const ExecCtx& c, const Launch& l) {
     attr_set = true;
   }
   interp_kernel<T><<<1, kInterpWarps * 32, smem, c.stream>>>(p.d_steps, p.d_interp_recs + (size_t)l.rec_off * kInterpRecBytes,
-                                                            l.first_step, l.last_step, d,
+                                                            p.d_interp_pre + l.pre_off, l.pre_n, l.first_step, l.last_step, d,
                                                             c.out_mode == CTN_OUT_DENSE, c.log_scale_out, c.flags_out);
   return cudaGetLastError();
 }

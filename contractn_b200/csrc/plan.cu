@@ -546,6 +546,13 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
       p.modes.insert(p.modes.end(), ls.out_modes.begin(), ls.out_modes.end());
       p.modes.insert(p.modes.end(), ls.k_modes.begin(), ls.k_modes.end());
       if (!ls.fused_consumer) sd.kind = (ls.tiny && allow_interp) ? kInterp : kGeneric;
+      if (sd.kind == kInterp && sd.n_in == 2) {
+        // pairwise step whose offsets fit 32 bits: the interpreter's short path (sd.tracked doubles as its flag)
+        int64_t span[2] = {0, 0};
+        for (int32_t m = sd.mode_off; m < (int32_t)p.modes.size(); ++m)
+          for (int i = 0; i < 2; ++i) span[i] += (p.modes[m].extent - 1) * p.modes[m].stride[i];
+        sd.tracked = span[0] < (1ll << 30) && span[1] < (1ll << 30);
+      }
       if (sd.kind == kGeneric && allow_gemm && ls.has_gemm) {
         if (int sk = skinny_config(p, sd, ls.gemm)) {
           sd.kind = kGemm;
@@ -611,6 +618,7 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
         if (i < sd.n_in) {
           auto it = producer.find(sd.in_slot[i]);
           if (it != producer.end() && it->second >= first) sd.dep[i] = it->second - first;
+          else if (p.slots[sd.in_slot[i]].operand >= 0) sd.dep[i] = -2;  // caller's operand: never rescaled
         }
       }
     }
@@ -656,6 +664,32 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
         if (pooled && k < sdv.n_in && sdv.dep[k] >= 0) sdv.smem_in[k] = p.steps[l.first_step + sdv.dep[k]].smem_out;
       }
     }
+    // Inputs that come from OUTSIDE the launch (operands, earlier intermediates) are staged into the
+    // pool once at kernel start when they are small: a dependent chain then never waits for an L2
+    // round trip.  The whole address span is copied, so the step's element strides stay valid.
+    l.pre_off = (int32_t)p.interp_pre.size();
+    if (pooled) {
+      std::map<int32_t, int32_t> staged;  // slot -> pool offset (shared operands are staged once)
+      for (int32_t i = l.first_step; i <= l.last_step; ++i) {
+        StepDev& sdv = p.steps[i];
+        for (int k = 0; k < sdv.n_in; ++k) {
+          if (sdv.dep[k] >= 0) continue;
+          const Slot& sl = p.slots[sdv.in_slot[k]];
+          auto it = staged.find(sdv.in_slot[k]);
+          if (it != staged.end()) { sdv.smem_in[k] = it->second; continue; }
+          if (sl.numel == 0) continue;
+          int64_t span = 1;
+          for (size_t a = 0; a < sl.extents.size(); ++a) span += (sl.extents[a] - 1) * sl.strides[a];
+          const size_t bytes = align_up((size_t)span * p.elem, 16);
+          if (span > 512 || total + bytes > (size_t)kInterpPoolBytes) continue;
+          staged[sdv.in_slot[k]] = (int32_t)total;
+          sdv.smem_in[k] = (int32_t)total;
+          p.interp_pre.push_back(InterpPreload{sdv.in_slot[k], (int32_t)total, (int32_t)span, 0});
+          total += bytes;
+        }
+      }
+    }
+    l.pre_n = (int32_t)p.interp_pre.size() - l.pre_off;
     l.smem_pool = pooled ? (int32_t)std::max<size_t>(total, 16) : 0;
     // packed records: descriptor + modes of a step in one 1 KB block the kernel fetches with cp.async
     static_assert(sizeof(StepDev) <= 256, "StepDev must fit the record header");
@@ -703,6 +737,7 @@ static int upload_plan(Plan& p) {
   CTN_CUDA(up((void**)&p.d_gemms, p.gemms.data(), p.gemms.size() * sizeof(GemmDev)));
   CTN_CUDA(up((void**)&p.d_slot_list, p.slot_list.data(), p.slot_list.size() * sizeof(int32_t)));
   CTN_CUDA(up((void**)&p.d_interp_recs, p.interp_recs.data(), p.interp_recs.size()));
+  CTN_CUDA(up((void**)&p.d_interp_pre, p.interp_pre.data(), p.interp_pre.size() * sizeof(InterpPreload)));
   return CTN_OK;
 }
 
@@ -778,6 +813,7 @@ void ctn_plan_destroy(ctn_plan* plan) {
     cudaFree(p.d_gemms);
     cudaFree(p.d_slot_list);
     cudaFree(p.d_interp_recs);
+    cudaFree(p.d_interp_pre);
     cudaFree(p.h_ws);
     cudaFree(p.h_out);
     cudaFree(p.h_log);
