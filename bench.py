@@ -336,7 +336,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "contractions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "api": "TN.make_contract_fun()(params, inputs) on pinned numpy arrays"},
-            "gpu_launches": (plan.num_launches + 1) * args.steps,  # chain + materialize + state-init kernel per step
+            # chain + materialize + state-init kernel per step (+ shard-stats and merge kernels when sharded)
+            "gpu_launches": (plan.num_launches + 1 + (2 if world > 1 else 0)) * args.steps,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
