@@ -17,6 +17,7 @@ is NO CPU fallback: if the library or a B200 is missing the calls raise.
 from __future__ import annotations
 
 import ctypes
+import operator
 import os
 import threading
 from collections import OrderedDict
@@ -231,12 +232,13 @@ class Plan:
                 pass
 
     # -- host buffers in, host buffers out ---------------------------------
-    def execute_host(self, arrays, out_mode=CTN_OUT_SPLIT):
+    def execute_host(self, arrays, out_mode=CTN_OUT_SPLIT, ptrs=None):
         """Run on host ``numpy`` arrays (copies in and out).  Returns
         ``(result, log_scale, flags)``."""
         n = len(self.shapes)
         assert len(arrays) == n
-        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        if ptrs is None:
+            ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrays])
         out = np.empty(self.out_shape, dtype=self.dtype)
         log_scale = ctypes.c_double(0.0)
         flags = ctypes.c_int32(0)
@@ -358,16 +360,40 @@ def _elem_strides(a):
     return tuple(int(s // item) for s in a.strides)
 
 
+# Networks of many small tensors (cfg 1: 1001 operands) spend milliseconds per call on per-operand
+# Python work (dtype, strides, ctypes pointers).  When a call passes the SAME array objects as the
+# previous one -- what ``TN.contract()`` / ``contract_fun(tn.params, ...)`` do -- that work is reused:
+# the bundle keeps the arrays alive (so the pointers stay valid) and is re-validated by identity,
+# shape and strides.  Only unconverted operands are cached (values are always read from the caller's buffers).
+_BUNDLE_MIN_OPERANDS = 16
+_BUNDLE_MAX_BYTES = 16 << 20
+_bundle = None
+
+
 def _run_numpy(arrays, contraction_list):
-    dtype = _compute_dtype([np.asarray(a).dtype for a in arrays])
-    arrays = [_prep_numpy(a, dtype) for a in arrays]
-    shapes = tuple(a.shape for a in arrays)
-    strides = tuple(_elem_strides(a) for a in arrays)
-    plan = get_plan(contraction_list, shapes, dtype, strides=strides)
-    out, log_scale, flags = plan.execute_host(arrays)
+    global _bundle
+    b = _bundle
+    if (b is not None and b[0] is contraction_list and len(arrays) == len(b[1])
+            and all(map(operator.is_, arrays, b[1]))
+            and tuple([a.shape for a in arrays]) == b[2] and tuple([a.strides for a in arrays]) == b[3]):
+        arrays, shapes, plan, ptrs, dtype, strides = b[1], b[2], b[4], b[5], b[6], b[7]
+    else:
+        src = arrays
+        dtype = _compute_dtype({np.asarray(a).dtype for a in arrays})
+        arrays = [_prep_numpy(a, dtype) for a in arrays]
+        shapes = tuple([a.shape for a in arrays])
+        strides = tuple([_elem_strides(a) for a in arrays])
+        plan = get_plan(contraction_list, shapes, dtype, strides=strides)
+        ptrs = (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        _bundle = None
+        if (len(arrays) >= _BUNDLE_MIN_OPERANDS and all(map(operator.is_, arrays, src))
+                and sum(a.nbytes for a in arrays) <= _BUNDLE_MAX_BYTES):
+            _bundle = (contraction_list, list(arrays), shapes, tuple([a.strides for a in arrays]), plan, ptrs,
+                       dtype, strides)
+    out, log_scale, flags = plan.execute_host(arrays, ptrs=ptrs)
     if flags & CTN_RESULT_DEGENERATE:
         exact = get_plan(contraction_list, shapes, dtype, strides=strides, flags=CTN_PLAN_EXACT_STEPS)
-        out, log_scale, flags = exact.execute_host(arrays)
+        out, log_scale, flags = exact.execute_host(arrays, ptrs=ptrs)
     return out, np.array(log_scale, dtype=np.float64)
 
 

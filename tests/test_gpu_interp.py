@@ -101,3 +101,20 @@ def test_tiny_norms_skip_rescale_inside_interpreter(gpu_engine):
     T, c = gpu_engine.core_contract(ops, lst)
     assert float(ref_c) == 0.0 and float(c) == 0.0
     np.testing.assert_allclose(T, ref_T, rtol=1e-12)
+
+
+def test_repeated_calls_reuse_host_bundle_but_read_fresh_values(gpu_engine):
+    """The host path caches per-operand bookkeeping between calls on the same array objects; values
+    are always read from the caller's buffers, and a replaced operand drops the cache."""
+    rng = np.random.default_rng(21)
+    einstr, ops = _chain(40, 3, rng, np.float64)
+    lst = planner.contract_path(einstr, *[o.shape for o in ops])[1]
+    for trial in range(3):
+        ref_T, ref_c = oracle.core_contract(ops, lst)
+        T, c = gpu_engine.core_contract(ops, lst)
+        assert_split_close(T, c, ref_T, ref_c, False, what=f"trial {trial}")
+        ops[7][...] = rng.uniform(0.5, 1.5, ops[7].shape)      # in-place update, same object
+    ops[3] = np.asfortranarray(rng.uniform(0.5, 1.5, (3, 3)))  # new object, different strides
+    ref_T, ref_c = oracle.core_contract(ops, lst)
+    T, c = gpu_engine.core_contract(ops, lst)
+    assert_split_close(T, c, ref_T, ref_c, False, what="replaced operand")
