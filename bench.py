@@ -37,7 +37,7 @@ METRIC = "contractions/s (cfg2: order-101 copy hub x 100 (2,B) f64, B=2^20 batch
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="evaluations per GPU (default 2^20)")
@@ -274,6 +274,10 @@ def main():
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        # ranks leave the host barrier up to ~1 ms apart; a device-side collective right before the start
+        # event lines the streams up, so that skew is not charged to the first merge of the timed steps
+        dist.all_reduce(torch.zeros(1, device=dev))
     ev0.record()
     for _ in range(args.steps):
         out, tail = step_device()
