@@ -551,6 +551,40 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
         qsb = (uint32_t)km.stride[1];
       }
     }
+    // Wider short path (pairwise, <= 128 outputs, <= 2 summed modes): up to four outputs per lane, same idea.
+    const bool quick4 = !quick && out_s != nullptr && s.tracked && numel <= 128 && s.n_k_modes <= 2;
+    uint32_t wa[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+    uint32_t w1n = 1, w1a = 0, w1b = 0, w2n = 1, w2a = 0, w2b = 0;
+    if (quick4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t rem = (uint32_t)(lane + 32 * j);
+        if ((int)rem < numel) {
+          uint32_t oa = 0, ob = 0;
+          for (int m = s.n_out_modes - 1; m > 0; --m) {
+            const uint32_t e = (uint32_t)modes[m].extent;
+            const uint32_t q = rem / e, idx = rem - q * e;
+            rem = q;
+            oa += idx * (uint32_t)modes[m].stride[0];
+            ob += idx * (uint32_t)modes[m].stride[1];
+          }
+          if (s.n_out_modes > 0) {
+            oa += rem * (uint32_t)modes[0].stride[0];
+            ob += rem * (uint32_t)modes[0].stride[1];
+          }
+          wa[j] = oa;
+          wb[j] = ob;
+        }
+      }
+      const ModeDev* km = modes + s.n_out_modes;
+      if (s.n_k_modes >= 1) {
+        const ModeDev& in_m = km[s.n_k_modes - 1];
+        w2n = (uint32_t)in_m.extent; w2a = (uint32_t)in_m.stride[0]; w2b = (uint32_t)in_m.stride[1];
+      }
+      if (s.n_k_modes == 2) {
+        w1n = (uint32_t)km[0].extent; w1a = (uint32_t)km[0].stride[0]; w1b = (uint32_t)km[0].stride[1];
+      }
+    }
     // pending scales of inputs made by earlier launches: loaded before the wait, off the dependency chain
     // (the first two inputs are handled in registers: an 8-way predicated loop over the record costs
     // ~35 cycles per slot on the critical path)
@@ -618,6 +652,25 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
           const T r = (T)(acc * alpha);
           out_s[lane] = r;
           local = fabs((double)r);
+        }
+      } else if (quick4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = lane + 32 * j;
+          if (o < numel) {
+            const T* a = in[0] + wa[j];
+            const T* b = in[1] + wb[j];
+            double acc = 0.0;
+            for (uint32_t k1 = 0; k1 < w1n; ++k1) {
+              const T* a1 = a + k1 * w1a;
+              const T* b1 = b + k1 * w1b;
+#pragma unroll 2
+              for (uint32_t k2 = 0; k2 < w2n; ++k2) acc = fma((double)a1[k2 * w2a], (double)b1[k2 * w2b], acc);
+            }
+            const T r = (T)(acc * alpha);
+            out_s[o] = r;
+            local += fabs((double)r);
+          }
         }
       } else if (s.tracked) {
         for (int o = lane; o < numel; o += 32) {
