@@ -80,7 +80,8 @@ struct StepDev {
   int32_t gemm_off;    // index into the plan's GemmDev table (-1 = none)
   int32_t ticket;      // index of this step's arrival counter
   int32_t is_final;    // output of the whole plan
-  int32_t tracked;     // chain: per-element exponent tracking (n_in > 2); interp: pairwise 32-bit short path
+  int32_t tracked;     // chain: per-element exponent tracking (n_in > 2); interp: pairwise 32-bit short path;
+                       // generic: few outputs x long sum -> dot kernel (partials at scratch_off)
   int32_t dep[kMaxIn]; // interp: launch-local index of the step producing input i (-1: ready at launch)  (-1: made by an earlier launch, -2: operand)
   int32_t smem_out;    // interp: byte offset of this step's output in the launch's shared-memory pool (-1: none)
   int32_t smem_in[kMaxIn];  // interp: byte offset of input i in that pool (-1: read it from global memory)
@@ -190,6 +191,8 @@ struct PtrChunk {
   void* p[kInitChunk];
 };
 cudaError_t launch_init_state(const Plan& plan, char* ws, cudaStream_t stream, const void* const* slot_ptrs);
+constexpr int kDotMaxOut = 16;          // dot kernel: at most this many outputs ...
+constexpr int64_t kDotMinK = 1 << 15;   // ... each a sum over at least this many terms
 constexpr int kShardStatBlocks = 148;  // CTN_SHARD_STATS_WORDS = 3 + kShardStatBlocks + 1 doubles
 cudaError_t launch_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws,
                                cudaStream_t stream);

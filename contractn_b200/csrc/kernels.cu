@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(kThreads) generic_step_kernel(const StepDev* _
 // and its threads run along the innermost mode, so loads and stores are
 // coalesced whenever that mode is contiguous and no div/mod is left in the loop.
 constexpr int kRowsKTable = 512;  // summed-mode offsets kept in shared memory up to this many
-constexpr int kRowsPerItem = 4;
+constexpr int kRowsPerItem = 4;      // default
+constexpr int kRowsPerItemWide = 16; // plenty of rows: fewer barriers and row decodes per byte moved
 
-template <typename T, int NIN, typename ACC>
+template <typename T, int NIN, typename ACC, int kRowsPerItem>
 __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* __restrict__ steps,
                                                                 const ModeDev* __restrict__ all_modes, int step_idx,
                                                                 DevState d) {
@@ -288,12 +289,23 @@ __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* _
     __syncthreads();
     if (threadIdx.x < NIN * kRowsPerItem) {
       const int i = threadIdx.x % NIN, rr = threadIdx.x / NIN;
-      int64_t o = 0, rem = row0 + rr;
-      for (int m = n_outer - 1; m >= 0; --m) {
-        const int64_t e = modes[m].extent;
-        const int64_t idx = rem % e;
-        rem /= e;
-        o += idx * modes[m].stride[i];
+      int64_t o = 0;
+      if (n_rows <= 0x7fffffff) {  // 32-bit divisions: the 64-bit ones are a ~400-cycle subroutine each
+        uint32_t rem = (uint32_t)(row0 + rr);
+        for (int m = n_outer - 1; m >= 0; --m) {
+          const uint32_t e = (uint32_t)modes[m].extent;
+          const uint32_t q = rem / e, idx = rem - q * e;
+          rem = q;
+          o += (int64_t)idx * modes[m].stride[i];
+        }
+      } else {
+        int64_t rem = row0 + rr;
+        for (int m = n_outer - 1; m >= 0; --m) {
+          const int64_t e = modes[m].extent;
+          const int64_t idx = rem % e;
+          rem /= e;
+          o += idx * modes[m].stride[i];
+        }
       }
       row_base[rr][i] = o;
     }
@@ -355,13 +367,143 @@ __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* _
   }
 }
 
-template <typename T, typename ACC>
+// ---------------------------------------------------------------------------
+// dot kernel: <= kDotMaxOut outputs, each a sum over >= kDotMinK terms (inner products, norms, the
+// closing step of a closed network).  Every CTA streams a grid-strided share of the summed index,
+// per-(output, CTA) partials go to scratch, the last CTA adds them in a fixed order.
+// ---------------------------------------------------------------------------
+template <typename T, int NIN>
+__global__ void __launch_bounds__(kThreads) dot_kernel(const StepDev* __restrict__ steps,
+                                                       const ModeDev* __restrict__ all_modes, int step_idx,
+                                                       DevState d) {
+  __shared__ double red[33];
+  __shared__ bool last_block;
+  __shared__ int64_t obase[kDotMaxOut][NIN];
+  const StepDev& s = steps[step_idx];
+  const ModeDev* modes = all_modes + s.mode_off;
+  const ModeDev* km = modes + s.n_out_modes;
+  const int n_out = (int)s.out_numel, n_k_modes = s.n_k_modes;
+  const T* in[NIN];
+  double alpha = 1.0;
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) {
+    in[i] = (const T*)d.ptrs[s.in_slot[i]];
+    alpha *= d.inv_kappa[s.in_slot[i]];
+  }
+  if (threadIdx.x < n_out) {
+    int64_t o[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) o[i] = 0;
+    int rem = threadIdx.x;
+    for (int m = s.n_out_modes - 1; m >= 0; --m) {
+      const int e = (int)modes[m].extent;
+      const int idx = rem % e;
+      rem /= e;
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) o[i] += (int64_t)idx * modes[m].stride[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) obase[threadIdx.x][i] = o[i];
+  }
+  __syncthreads();
+  const ModeDev& inner = km[n_k_modes - 1];
+  const int64_t inner_n = inner.extent;
+  int64_t istr[NIN];
+#pragma unroll
+  for (int i = 0; i < NIN; ++i) istr[i] = inner.stride[i];
+  double acc[kDotMaxOut];
+#pragma unroll
+  for (int o = 0; o < kDotMaxOut; ++o) acc[o] = 0.0;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll 2
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < s.k_numel; k += gstride) {
+    int64_t koff[NIN];
+    if (n_k_modes == 1) {
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) koff[i] = k * istr[i];
+    } else {
+      int64_t rem = k / inner_n;
+      const int64_t j = k - rem * inner_n;
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) koff[i] = j * istr[i];
+      for (int m = n_k_modes - 2; m >= 0; --m) {
+        const int64_t e = km[m].extent;
+        const int64_t q = rem / e, idx = rem - q * e;
+        rem = q;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) koff[i] += idx * km[m].stride[i];
+      }
+    }
+    if (n_out == 1) {
+      double pr = (double)__ldg(in[0] + obase[0][0] + koff[0]);
+#pragma unroll
+      for (int i = 1; i < NIN; ++i) pr *= (double)__ldg(in[i] + obase[0][i] + koff[i]);
+      acc[0] += pr;
+    } else {
+#pragma unroll
+      for (int o = 0; o < kDotMaxOut; ++o) {
+        if (o < n_out) {
+          double pr = (double)__ldg(in[0] + obase[o][0] + koff[0]);
+#pragma unroll
+          for (int i = 1; i < NIN; ++i) pr *= (double)__ldg(in[i] + obase[o][i] + koff[i]);
+          acc[o] += pr;
+        }
+      }
+    }
+  }
+  double* scratch = (double*)(d.arena + s.scratch_off);
+#pragma unroll
+  for (int o = 0; o < kDotMaxOut; ++o) {
+    if (o < n_out) {
+      const double b = block_sum(acc[o], red);
+      if (threadIdx.x == 0) scratch[(size_t)o * gridDim.x + blockIdx.x] = b;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t t = atomicAdd(&d.tickets[s.ticket], 1u);
+    last_block = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last_block) return;
+  __threadfence();
+  T* out = (T*)d.ptrs[s.out_slot];
+  double norm = 0.0;
+  for (int o = 0; o < n_out; ++o) {
+    double part = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) part += __ldcg(&scratch[(size_t)o * gridDim.x + b]);
+    const double total = block_sum(part, red);  // fixed tree: the same bits every run
+    const T r = (T)(total * alpha);
+    if (threadIdx.x == 0) out[o] = r;
+    norm += fabs((double)r);
+  }
+  if (threadIdx.x == 0) {
+    record_scale(d, s.out_slot, norm, s.out_numel);
+    d.tickets[s.ticket] = 0;
+  }
+}
+
+template <typename T>
+static cudaError_t launch_dot(const ExecCtx& c, const Launch& l, int grid, int n_in) {
+  const Plan& p = *c.plan;
+  DevState d = dev_state(c);
+  switch (n_in) {
+    case 1: dot_kernel<T, 1><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d); break;
+    case 2: dot_kernel<T, 2><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d); break;
+    case 3: dot_kernel<T, 3><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d); break;
+    case 4: dot_kernel<T, 4><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+template <typename T, typename ACC, int RPI>
 static cudaError_t launch_rows(const ExecCtx& c, const Launch& l, int grid, int n_in) {
   const Plan& p = *c.plan;
   DevState d = dev_state(c);
-#define CTN_ROWS_CASE(N_)                                                                                         \
-  case N_:                                                                                                        \
-    generic_rows_kernel<T, N_, ACC><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d); \
+#define CTN_ROWS_CASE(N_)                                                                                              \
+  case N_:                                                                                                             \
+    generic_rows_kernel<T, N_, ACC, RPI><<<grid, kThreads, 0, c.stream>>>(p.d_steps, p.d_modes, l.first_step, d); \
     break;
   switch (n_in) {
     CTN_ROWS_CASE(1)
@@ -380,18 +522,31 @@ cudaError_t launch_generic(const ExecCtx& c, const Launch& l) {
   const StepDev& s = p.steps[l.first_step];
   DevState d = dev_state(c);
   const int64_t cap = std::min<int64_t>((int64_t)p.sm_count * 8, kMaxPartials);
+  if (s.tracked) {  // few outputs x long sum (set by the plan together with the scratch for the partials)
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((s.k_numel + 4 * kThreads - 1) / (4 * kThreads), cap));
+    return p.dtype == CTN_F32 ? launch_dot<float>(c, l, grid, s.n_in) : launch_dot<double>(c, l, grid, s.n_in);
+  }
   // long innermost output mode and few summed indices: row-wise kernel
   if (s.n_out_modes >= 1 && s.k_numel <= kRowsKTable && s.n_in <= 4) {
     const int64_t inner_n = p.modes[s.mode_off + s.n_out_modes - 1].extent;
     if (inner_n >= 64) {
       const int64_t n_rows = s.out_numel / inner_n;
-      const int64_t work = ((n_rows + kRowsPerItem - 1) / kRowsPerItem) * ((inner_n + kThreads - 1) / kThreads);
+      const int64_t chunks = (inner_n + kThreads - 1) / kThreads;
+      // wide items only when they still give every CTA of a full grid several items
+      const int64_t work_wide = ((n_rows + kRowsPerItemWide - 1) / kRowsPerItemWide) * chunks;
+      const bool wide = work_wide >= 4 * cap;
+      const int64_t work = wide ? work_wide : ((n_rows + kRowsPerItem - 1) / kRowsPerItem) * chunks;
       const int grid = (int)std::max<int64_t>(1, std::min(work, cap));
       // float data: short sums stay in fp32 (what the reference's einsum does too);
       // long ones are accumulated in fp64
-      if (p.dtype == CTN_F64) return launch_rows<double, double>(c, l, grid, s.n_in);
-      if (s.k_numel <= 64) return launch_rows<float, float>(c, l, grid, s.n_in);
-      return launch_rows<float, double>(c, l, grid, s.n_in);
+      if (wide) {
+        if (p.dtype == CTN_F64) return launch_rows<double, double, kRowsPerItemWide>(c, l, grid, s.n_in);
+        if (s.k_numel <= 64) return launch_rows<float, float, kRowsPerItemWide>(c, l, grid, s.n_in);
+        return launch_rows<float, double, kRowsPerItemWide>(c, l, grid, s.n_in);
+      }
+      if (p.dtype == CTN_F64) return launch_rows<double, double, kRowsPerItem>(c, l, grid, s.n_in);
+      if (s.k_numel <= 64) return launch_rows<float, float, kRowsPerItem>(c, l, grid, s.n_in);
+      return launch_rows<float, double, kRowsPerItem>(c, l, grid, s.n_in);
     }
   }
   int64_t blocks = (s.out_numel + kThreads - 1) / kThreads;

@@ -553,7 +553,10 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
           for (int i = 0; i < 2; ++i) span[i] += (p.modes[m].extent - 1) * p.modes[m].stride[i];
         sd.tracked = span[0] < (1ll << 30) && span[1] < (1ll << 30);
       }
-      if (sd.kind == kGeneric && allow_gemm && ls.has_gemm) {
+      // few outputs, each a long sum (DOT class, <a|b>): grid-wide reduction kernel, not a 1x1 GEMM
+      const bool dot_like = sd.kind == kGeneric && sd.n_in <= 4 && ls.out_numel <= kDotMaxOut && ls.k_numel >= kDotMinK;
+      if (dot_like) sd.tracked = 1;
+      if (sd.kind == kGeneric && !dot_like && allow_gemm && ls.has_gemm) {
         if (int sk = skinny_config(p, sd, ls.gemm)) {
           sd.kind = kGemm;
           sd.gemm_off = (int32_t)p.gemms.size();
@@ -585,6 +588,11 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
         sd.scratch_off = (int64_t)arena.alloc(scratch_bytes);
         p.gemms[sd.gemm_off].scratch_off = sd.scratch_off;
       }
+    }
+    if (sd.kind == kGeneric && sd.tracked) {
+      // dot kernel: one partial per (output, CTA)
+      scratch_bytes = (size_t)kDotMaxOut * kMaxPartials * sizeof(double);
+      sd.scratch_off = (int64_t)arena.alloc(scratch_bytes);
     }
     if (sd.kind == kChain && sd.tracked) {
       // one exponent per tile of the chain output (tile = 1024 f64 / 2048 f32 at most;

@@ -21,7 +21,8 @@ CASES = [
     ("ab,bc->ac", [(16, 24), (24, 1000)], "narrow M: 32x128 tiles"),
     ("ab,b->a", [(512, 300), (300,)], "GEMV"),
     ("a,ab->b", [(300,), (300, 512)], "vector-matrix"),
-    ("ab,ab->", [(300, 400), (300, 400)], "DOT: split-K"),
+    ("ab,ab->", [(300, 400), (300, 400)], "DOT: reduction kernel"),
+    ("ak,bk->ab", [(8, 120000), (8, 120000)], "8x8 output, K = 120000: split-K"),
     ("ab,ba->", [(300, 400), (400, 300)], "transposed DOT"),
     ("abc,bcd->ad", [(40, 30, 20), (30, 20, 50)], "two contiguous summed modes fuse"),
     ("abc,cbd->ad", [(40, 30, 20), (20, 30, 50)], "two summed modes, not fusable in B"),
@@ -61,7 +62,8 @@ def test_gemm_kinds_are_selected(gpu_engine):
         return gpu_engine.Plan(lst, shapes, np.float64).launch_kinds
 
     assert kinds("ab,bc->ac", [(256, 128), (128, 192)]) == ("gemm", "finalize")
-    assert kinds("ab,ab->", [(300, 400)] * 2) == ("gemm", "gemm_reduce", "finalize")
+    assert kinds("ab,ab->", [(300, 400)] * 2) == ("generic", "finalize")  # DOT class: grid-wide reduction kernel
+    assert kinds("ak,bk->ab", [(8, 120000)] * 2) == ("gemm", "gemm_reduce", "finalize")  # small output, long K
     assert kinds("bps,bp->bs", [(300, 2, 64), (300, 2)]) == ("generic", "finalize")
     assert kinds("ab,bc->ac", [(4100, 40), (40, 24)]) == ("gemm", "finalize")  # skinny variant
 

@@ -118,3 +118,35 @@ def test_repeated_calls_reuse_host_bundle_but_read_fresh_values(gpu_engine):
     ref_T, ref_c = oracle.core_contract(ops, lst)
     T, c = gpu_engine.core_contract(ops, lst)
     assert_split_close(T, c, ref_T, ref_c, False, what="replaced operand")
+
+
+DOT_CASES = [
+    ("ab,ab->", [(300, 400), (300, 400)]),           # inner product, one fused summed mode
+    ("ab,ba->", [(300, 400), (400, 300)]),           # two summed modes that do not fuse
+    ("abk,bk->a", [(4, 30, 2000), (30, 2000)]),      # several outputs
+    ("ak,ak->a", [(8, 50000), (8, 50000)]),          # batch index kept, long sum
+    ("k,k,k->", [(100000,), (100000,), (100000,)]),  # n-ary
+    ("abc->", [(40, 50, 60)]),                       # single-operand full reduction
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("einstr,shapes", DOT_CASES, ids=[c[0] for c in DOT_CASES])
+def test_dot_class_steps(gpu_engine, einstr, shapes, dtype):
+    """Few outputs, each a long sum (DOT class of einsum.py:347-384): the grid-wide reduction kernel."""
+    rng = np.random.default_rng(len(einstr) + len(shapes))
+    ops = [rng.uniform(0.5, 1.5, s).astype(dtype) for s in shapes]
+    lst = planner.contract_path(einstr, *shapes, optimize=tuple([tuple(range(len(shapes)))]))[1]
+    assert len(lst) == 1
+    ref_T, ref_c = oracle.core_contract(ops, lst)
+    T, c = gpu_engine.core_contract(ops, lst)
+    assert_split_close(T, c, ref_T, ref_c, dtype == np.float32, what=einstr)
+    # signed data: compare the dense value norm-wise
+    ops = [rng.uniform(-1, 1, s).astype(dtype) for s in shapes]
+    ref_T, ref_c = oracle.core_contract(ops, lst)
+    T, c = gpu_engine.core_contract(ops, lst)
+    ref = np.asarray(ref_T, dtype=np.float64) * np.exp(float(ref_c))
+    got = np.asarray(T, dtype=np.float64) * np.exp(float(c))
+    scale = np.sqrt(float(np.prod(shapes[0])))  # cancellation: error relative to the size of the terms
+    tol = (1e-4 if dtype == np.float32 else 1e-11) * scale
+    assert np.abs(got - ref).max() <= tol, (got, ref)
