@@ -415,8 +415,31 @@ __global__ void __launch_bounds__(kThreads) dot_kernel(const StepDev* __restrict
 #pragma unroll
   for (int o = 0; o < kDotMaxOut; ++o) acc[o] = 0.0;
   const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  int64_t k_first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_k_modes == 1 && n_out == 1) {
+    // plain inner product: four independent strided loads per operand in flight per thread
+    const T* p[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) p[i] = in[i] + obase[0][i];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (; k_first + 3 * gstride < s.k_numel; k_first += 4 * gstride) {
+      double v0 = (double)__ldg(p[0] + k_first * istr[0]);
+      double v1 = (double)__ldg(p[0] + (k_first + gstride) * istr[0]);
+      double v2 = (double)__ldg(p[0] + (k_first + 2 * gstride) * istr[0]);
+      double v3 = (double)__ldg(p[0] + (k_first + 3 * gstride) * istr[0]);
+#pragma unroll
+      for (int i = 1; i < NIN; ++i) {
+        v0 *= (double)__ldg(p[i] + k_first * istr[i]);
+        v1 *= (double)__ldg(p[i] + (k_first + gstride) * istr[i]);
+        v2 *= (double)__ldg(p[i] + (k_first + 2 * gstride) * istr[i]);
+        v3 *= (double)__ldg(p[i] + (k_first + 3 * gstride) * istr[i]);
+      }
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    acc[0] = (a0 + a1) + (a2 + a3);
+  }
 #pragma unroll 2
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < s.k_numel; k += gstride) {
+  for (int64_t k = k_first; k < s.k_numel; k += gstride) {
     int64_t koff[NIN];
     if (n_k_modes == 1) {
 #pragma unroll
