@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) generic_step_kernel(const StepDev* _
 // coalesced whenever that mode is contiguous and no div/mod is left in the loop.
 constexpr int kRowsKTable = 512;  // summed-mode offsets kept in shared memory up to this many
 constexpr int kRowsPerItem = 4;      // default
-constexpr int kRowsPerItemWide = 16; // plenty of rows: fewer barriers and row decodes per byte moved
+constexpr int kRowsPerItemWide = 8;  // plenty of rows: fewer barriers and row decodes per byte moved
 
 template <typename T, int NIN, typename ACC, int kRowsPerItem>
 __global__ void __launch_bounds__(kThreads) generic_rows_kernel(const StepDev* __restrict__ steps,
