@@ -267,12 +267,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        step_device()
-    sync_all()
+    # the clock sampler (one long-running nvidia-smi) is started BEFORE the warm-up and given time to
+    # print its first sample: its start-up queries take driver locks and would otherwise stall the
+    # first timed launches
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.perf_counter()
+        while sampler.proc is not None and not sampler.lines and time.perf_counter() - t_wait < 3.0:
+            time.sleep(0.02)
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         # ranks leave the host barrier up to ~1 ms apart; a device-side collective right before the start
