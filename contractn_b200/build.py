@@ -29,13 +29,27 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    built = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+def _source_digest():
+    """Content hash of everything the library is built from (mtimes do not survive a
+    snapshot copy to the GPU box; contents do)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
     deps.append(os.path.join(ROOT, "include", "ctn_b200.h"))
-    return any(os.path.getmtime(d) > built for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
+def _stale():
+    if not os.path.exists(LIB) or not os.path.exists(LIB + ".digest"):
+        return True
+    with open(LIB + ".digest") as f:
+        return f.read().strip() != _source_digest()
 
 
 def build_library(force=False, verbose=False):
@@ -50,6 +64,8 @@ def build_library(force=False, verbose=False):
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
     os.replace(LIB + ".tmp", LIB)
+    with open(LIB + ".digest", "w") as f:
+        f.write(_source_digest())
     if verbose:
         print(proc.stderr)
     return LIB

@@ -165,6 +165,7 @@ struct Plan {
   InterpPreload* d_interp_pre = nullptr;
   int device = 0;
   int sm_count = 148;
+  std::mutex host_mu;                     // serialises ctn_plan_execute_host (plan-owned staging below)
   // host-buffer path scratch (ctn_plan_execute_host)
   void* h_ws = nullptr;
   size_t h_ws_bytes = 0;
@@ -215,5 +216,18 @@ cudaError_t launch_materialize(const ExecCtx& c, const Launch& l, bool vec_ok);
 bool gemm_supported(const Plan& p, const StepDev& s, const GemmDev& g);
 
 void set_cuda_error(cudaError_t e, const char* where);
+
+// cudaFuncSetAttribute is per device: remember per (kernel instantiation, device) that it was done.
+struct AttrOnce {
+  bool done[64] = {};
+  template <class K>
+  cudaError_t ensure(K kern, int device, int smem_bytes) {
+    const int i = device >= 0 && device < 64 ? device : 63;
+    if (done[i] && device < 63) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) done[i] = true;
+    return e;
+  }
+};
 
 }  // namespace ctn

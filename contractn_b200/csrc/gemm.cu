@@ -422,11 +422,10 @@ template <class Cfg, int LA, int LB>
 static cudaError_t launch_cfg(const ExecCtx& c, const Launch& l, const GemmDev& g) {
   const Plan& p = *c.plan;
   auto kern = gemm_f64_kernel<Cfg, LA, LB>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  static AttrOnce attr;  // per instantiation
+  {
+    cudaError_t e = attr.ensure(kern, p.device, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int64_t tilesM = (g.M + Cfg::BM - 1) / Cfg::BM, tilesN = (g.N + Cfg::BN - 1) / Cfg::BN;
   const int64_t total = g.B * tilesM * tilesN * g.splits;

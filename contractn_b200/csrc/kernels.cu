@@ -936,11 +936,10 @@ static cudaError_t launch_interp_t(const ExecCtx& c, const Launch& l) {
   const int n_steps = l.last_step - l.first_step + 1;
   const size_t smem = (size_t)kInterpWarps * 2 * kInterpRecBytes + (((size_t)n_steps * 4 + 15) & ~(size_t)15) +
                       (size_t)n_steps * 8 + (size_t)l.smem_pool + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(interp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  static AttrOnce attr;  // per instantiation
+  {
+    cudaError_t e = attr.ensure(interp_kernel<T>, p.device, 220 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   interp_kernel<T><<<1, kInterpWarps * 32, smem, c.stream>>>(p.d_steps, p.d_interp_recs + (size_t)l.rec_off * kInterpRecBytes,
                                                             p.d_interp_pre + l.pre_off, l.pre_n, l.first_step, l.last_step, d,

@@ -880,6 +880,12 @@ static int execute_impl(const ctn_plan* plan, const void* const* operands, void*
   if (out_mode != CTN_OUT_SPLIT && out_mode != CTN_OUT_DENSE) return CTN_ERR_INVALID;
   const Plan& p = plan->p;
   if (p.device < 0) return CTN_ERR_NO_DEVICE;
+  {
+    // the plan's descriptor tables live on p.device: launching from another current device would
+    // hand kernels on that device pointers they cannot dereference
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != p.device) return CTN_ERR_INVALID;
+  }
   cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
   if (((uintptr_t)ws & 255) != 0) return CTN_ERR_INVALID;
@@ -991,7 +997,20 @@ int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void
   if (!plan || !operands_host || !out_host || !log_scale_host) return CTN_ERR_INVALID;
   Plan& p = plan->p;
   if (p.device < 0) return CTN_ERR_NO_DEVICE;
-  CTN_CUDA(cudaSetDevice(p.device));
+  // the staging buffers below belong to the plan: one host-path execution at a time
+  std::lock_guard<std::mutex> guard(p.host_mu);
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } dev_guard;
+  {
+    int cur = -1;
+    CTN_CUDA(cudaGetDevice(&cur));
+    if (cur != p.device) {
+      dev_guard.prev = cur;
+      CTN_CUDA(cudaSetDevice(p.device));
+    }
+  }
   size_t ws_bytes = ctn_plan_workspace_bytes(plan);
   if (!p.h_ws) {
     CTN_CUDA(cudaMalloc(&p.h_ws, ws_bytes));

@@ -83,15 +83,14 @@ _lib_lock = threading.Lock()
 
 
 def load_library():
-    """dlopen ``libctn_b200.so`` (building it first if the sources are newer)."""
+    """dlopen ``libctn_b200.so`` (rebuilding it first when the sources changed)."""
     global _lib
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(_LIB_PATH):
-            from .build import build_library
+        from .build import build_library
 
-            build_library()
+        build_library()  # no-op unless the library is missing or older than its sources (content digest)
         lib = ctypes.CDLL(_LIB_PATH)
         vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
         lib.ctn_plan_create.argtypes = [ctypes.POINTER(_PlanDesc), ctypes.POINTER(vp)]
@@ -163,6 +162,7 @@ class Plan:
     def __init__(self, contraction_list, shapes, dtype, strides=None, flags=0):
         lib = load_library()
         self._lib = lib
+        self._lock = threading.Lock()  # one workspace / staging set per plan: executions are serialised
         self.dtype = np.dtype(dtype)
         if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
             raise NotImplementedError(f"dtype {self.dtype} is not supported by the B200 engine")
@@ -242,11 +242,12 @@ class Plan:
         out = np.empty(self.out_shape, dtype=self.dtype)
         log_scale = ctypes.c_double(0.0)
         flags = ctypes.c_int32(0)
-        _check(
-            self._lib.ctn_plan_execute_host(self._h, ptrs, out.ctypes.data, ctypes.byref(log_scale),
-                                            ctypes.byref(flags), out_mode),
-            "ctn_plan_execute_host",
-        )
+        with self._lock:
+            _check(
+                self._lib.ctn_plan_execute_host(self._h, ptrs, out.ctypes.data, ctypes.byref(log_scale),
+                                                ctypes.byref(flags), out_mode),
+                "ctn_plan_execute_host",
+            )
         return out, log_scale.value, flags.value
 
     # -- device buffers (torch CUDA tensors or raw pointers) ----------------
@@ -269,28 +270,31 @@ class Plan:
         import torch
 
         device = tensors[0].device
-        _, _ws, ws_ptr, tail = self._device_scratch(device)
-        tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
-        if out is None:
-            out = torch.empty(self.out_shape, dtype=tdtype, device=device)
-        n = len(self.shapes)
-        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
-        if stream is None:
-            stream = torch.cuda.current_stream(device).cuda_stream
-        if timed:
-            ms = (ctypes.c_float * max(1, self.num_launches))()
+        # the plan's descriptor tables live on the device that was current when it was created
+        # (get_plan keys on it); launches go to that device whatever the caller's current one is
+        with self._lock, torch.cuda.device(device):
+            _, _ws, ws_ptr, tail = self._device_scratch(device)
+            tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
+            if out is None:
+                out = torch.empty(self.out_shape, dtype=tdtype, device=device)
+            n = len(self.shapes)
+            ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+            if stream is None:
+                stream = torch.cuda.current_stream(device).cuda_stream
+            if timed:
+                ms = (ctypes.c_float * max(1, self.num_launches))()
+                _check(
+                    self._lib.ctn_plan_execute_timed(self._h, ptrs, out.data_ptr(), tail.data_ptr(),
+                                                     tail.data_ptr() + 8, ws_ptr, out_mode, stream, ms),
+                    "ctn_plan_execute_timed",
+                )
+                return out, tail, [float(ms[i]) for i in range(self.num_launches)]
             _check(
-                self._lib.ctn_plan_execute_timed(self._h, ptrs, out.data_ptr(), tail.data_ptr(),
-                                                 tail.data_ptr() + 8, ws_ptr, out_mode, stream, ms),
-                "ctn_plan_execute_timed",
+                self._lib.ctn_plan_execute(self._h, ptrs, out.data_ptr(), tail.data_ptr(), tail.data_ptr() + 8,
+                                           ws_ptr, out_mode, stream),
+                "ctn_plan_execute",
             )
-            return out, tail, [float(ms[i]) for i in range(self.num_launches)]
-        _check(
-            self._lib.ctn_plan_execute(self._h, ptrs, out.data_ptr(), tail.data_ptr(), tail.data_ptr() + 8,
-                                       ws_ptr, out_mode, stream),
-            "ctn_plan_execute",
-        )
-        return out, tail
+            return out, tail
 
     @property
     def may_degenerate(self):
@@ -310,22 +314,36 @@ def _hashable_list(contraction_list):
     return tuple((tuple(c[0]), c[2]) for c in contraction_list)
 
 
-def get_plan(contraction_list, shapes, dtype, strides=None, flags=0):
+_plan_cache_lock = threading.Lock()
+
+
+def get_plan(contraction_list, shapes, dtype, strides=None, flags=0, device=None):
+    """Cached :class:`Plan`.  ``device`` is the CUDA device index the plan is bound to (its
+    descriptor tables are allocated there); ``None`` = the current device (host-buffer path)."""
     key = (_hashable_list(contraction_list), tuple(shapes), np.dtype(dtype).str,
-           None if strides is None else tuple(strides), flags)
-    plan = _plan_cache.get(key)
-    if plan is None:
+           None if strides is None else tuple(strides), flags, device)
+    with _plan_cache_lock:
+        plan = _plan_cache.get(key)
+        if plan is not None:
+            _plan_cache.move_to_end(key)
+            return plan
+    if device is None:
         plan = Plan(contraction_list, shapes, dtype, strides=strides, flags=flags)
-        _plan_cache[key] = plan
+    else:
+        import torch
+
+        with torch.cuda.device(device):
+            plan = Plan(contraction_list, shapes, dtype, strides=strides, flags=flags)
+    with _plan_cache_lock:
+        plan = _plan_cache.setdefault(key, plan)
         if len(_plan_cache) > _PLAN_CACHE_SIZE:
             _plan_cache.popitem(last=False)
-    else:
-        _plan_cache.move_to_end(key)
     return plan
 
 
 def clear_plan_cache():
-    _plan_cache.clear()
+    with _plan_cache_lock:
+        _plan_cache.clear()
 
 
 # ---------------------------------------------------------------------------
@@ -370,7 +388,7 @@ _BUNDLE_MAX_BYTES = 16 << 20
 _bundle = None
 
 
-def _run_numpy(arrays, contraction_list):
+def _run_numpy(arrays, contraction_list, out_mode=CTN_OUT_SPLIT):
     global _bundle
     b = _bundle
     if (b is not None and b[0] is contraction_list and len(arrays) == len(b[1])
@@ -390,36 +408,45 @@ def _run_numpy(arrays, contraction_list):
                 and sum(a.nbytes for a in arrays) <= _BUNDLE_MAX_BYTES):
             _bundle = (contraction_list, list(arrays), shapes, tuple([a.strides for a in arrays]), plan, ptrs,
                        dtype, strides)
-    out, log_scale, flags = plan.execute_host(arrays, ptrs=ptrs)
+    out, log_scale, flags = plan.execute_host(arrays, out_mode=out_mode, ptrs=ptrs)
     if flags & CTN_RESULT_DEGENERATE:
         exact = get_plan(contraction_list, shapes, dtype, strides=strides, flags=CTN_PLAN_EXACT_STEPS)
-        out, log_scale, flags = exact.execute_host(arrays, ptrs=ptrs)
+        out, log_scale, flags = exact.execute_host(arrays, out_mode=out_mode, ptrs=ptrs)
     return out, np.array(log_scale, dtype=np.float64)
 
 
-def _run_torch(tensors, contraction_list, dense=False):
+def _run_torch(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
     import torch
 
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        # the reference's torch backend is plain differentiable torch ops; this engine has no
+        # backward plan, and silently detaching would hand a training loop zero gradients
+        raise NotImplementedError(
+            "contractn_b200 has no autograd through the device plan: call under torch.no_grad() "
+            "or pass detached tensors")
     if not tensors[0].is_cuda:
-        out, log_scale = _run_numpy([t.detach().numpy() for t in tensors], contraction_list)
+        out, log_scale = _run_numpy([t.detach().numpy() for t in tensors], contraction_list, out_mode)
         res = torch.from_numpy(np.ascontiguousarray(out))
         return res, torch.tensor(float(log_scale), dtype=res.dtype)
     tdt = torch.float64 if any(t.dtype == torch.float64 for t in tensors) else torch.float32
     if any(t.is_complex() for t in tensors):
         raise NotImplementedError("complex tensors are not supported by the B200 engine")
-    tensors = [t.detach().to(tdt) for t in tensors]
+    tensors = [t.detach() for t in tensors]
+    tensors = [t if t.dtype == tdt else t.to(tdt) for t in tensors]
     tensors = [t if all(s >= 0 for s in t.stride()) else t.contiguous() for t in tensors]
     shapes = tuple(tuple(t.shape) for t in tensors)
     strides = tuple(tuple(t.stride()) for t in tensors)
     ndt = np.float64 if tdt == torch.float64 else np.float32
-    plan = get_plan(contraction_list, shapes, ndt, strides=strides)
-    out, tail = plan.execute_device(tensors)
+    dev = tensors[0].device.index
+    plan = get_plan(contraction_list, shapes, ndt, strides=strides, device=dev)
+    out, tail = plan.execute_device(tensors, out_mode=out_mode)
     if plan.may_degenerate:
+        # one 4-byte read back: only plans with fused steps can raise the flag (see Plan.may_degenerate)
         flags = int(tail[1:2].view(torch.int32)[0].item())
         if flags & CTN_RESULT_DEGENERATE:
-            exact = get_plan(contraction_list, shapes, ndt, strides=strides, flags=CTN_PLAN_EXACT_STEPS)
-            out, tail = exact.execute_device(tensors)
-    return out, tail[0].clone().to(tdt)
+            exact = get_plan(contraction_list, shapes, ndt, strides=strides, flags=CTN_PLAN_EXACT_STEPS, device=dev)
+            out, tail = exact.execute_device(tensors, out_mode=out_mode)
+    return out, tail[0].to(tdt)
 
 
 def core_contract(operands, contract_list, backend=None, **einsum_kwargs):
@@ -462,16 +489,23 @@ def contract(*operands, **kwargs):
     contract_list = planner.cached_contract_list(
         einstr, shapes, optimize=optimize_arg, memory_limit=memory_limit, use_blas=use_blas
     )
-    result, log_scale = core_contract(ops, contract_list, **einsum_kwargs)
     if split_format:
-        return result, log_scale
-    # destabilize (einsum.py:110-114) with the operands' own array library
-    if _is_torch(result):
-        import torch
-
-        return result * torch.exp(log_scale)
-    with np.errstate(over="ignore"):
-        return result * np.exp(log_scale)
+        return core_contract(ops, contract_list, **einsum_kwargs)
+    # destabilize (einsum.py:110-114, 310): T-hat * exp(c), applied by the plan's last kernel
+    # (CTN_OUT_DENSE) -- no extra pass, no host arithmetic
+    ops = list(ops)
+    if einsum_kwargs.get("dtype") is not None:
+        ops = [np.asarray(o, dtype=einsum_kwargs["dtype"]) for o in ops]
+    if _is_torch(ops[0]):
+        return _run_torch(ops, contract_list, CTN_OUT_DENSE)[0]
+    dtype = _compute_dtype({np.asarray(a).dtype for a in ops})
+    if dtype == np.float32:
+        # numpy's own rule for float32 array * 0-d float64 register (einsum.py:114, 338) is a float64
+        # result: keep that dtype by multiplying the float32 mantissas on the host
+        result, log_scale = _run_numpy(ops, contract_list)
+        with np.errstate(over="ignore", invalid="ignore"):
+            return result * np.exp(log_scale)
+    return _run_numpy(ops, contract_list, CTN_OUT_DENSE)[0]
 
 
 def install(contractn_module=None):

@@ -15,9 +15,13 @@
  * Conventions
  *  - plain C, no C++/torch types; every function returns an int status
  *    (CTN_OK == 0) and never throws; ctn_status_string() explains a status.
- *  - the caller owns every data buffer.  A plan owns only immutable metadata
- *    (host structs + a device copy of the step descriptors), so one plan may be
- *    executed concurrently on distinct streams with distinct workspaces.
+ *  - the caller owns every data buffer passed to ctn_plan_execute().  For that
+ *    entry point a plan is immutable metadata (host structs + a copy of the step
+ *    descriptors on the device that was current at ctn_plan_create), so one plan
+ *    may be executed concurrently on distinct streams with distinct workspaces,
+ *    always with that same device current (CTN_ERR_INVALID otherwise).
+ *    ctn_plan_execute_host() additionally keeps staging buffers inside the plan;
+ *    calls on one plan are serialised by a mutex inside it.
  *  - execution is asynchronous on the given stream; no hidden synchronisation
  *    in ctn_plan_execute().  ctn_plan_execute_host() is synchronous.
  *  - element strides, not byte strides.  Outputs are C-contiguous in the order
@@ -151,7 +155,7 @@ int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, vo
 
 /* Same with HOST buffers: copies the operands to the device, runs the plan,
  * copies the result back and synchronises.  Device scratch is cached inside
- * the plan between calls (so this entry point is NOT re-entrant per plan).
+ * the plan between calls; calls on the same plan are serialised by a mutex inside it.
  * This is the call a ctypes/cgo/JNI binding over host arrays makes. */
 int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void* out_host,
                           double* log_scale_host, int32_t* flags_host, int out_mode);
