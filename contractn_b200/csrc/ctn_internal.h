@@ -62,7 +62,7 @@ struct GemmDev {
   // out[m, n'] = sum_r W[m, r] * X[m, (r, n')] is evaluated in the epilogue (in_slot[2] = W).
   // `n` then holds only the n' modes (sc = strides in `out`), N = prod(n'), and:
   int32_t fuse_pr;      // extent of r (0 = not fused; 2 or 4)
-  int32_t fuse_pad;
+  int32_t fuse_pad;     // gemm_tf32.cu: bit 0 = the output admits 16-byte stores
   int64_t fuse_sb;      // stride of r in B
   int64_t fuse_sw;      // stride of r in W
 };
@@ -209,7 +209,10 @@ int skinny_config(const Plan& p, const StepDev& s, const GemmDev& g);
 cudaError_t launch_skinny(const ExecCtx& c, const Launch& l);
 bool gemm_tf32_supported(const Plan& p, const StepDev& s, const GemmDev& g);
 void gemm_tf32_configure(const Plan& p, GemmDev& g);
-cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);
+cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned, bool c_aligned,
+                             const void* b_ptr);
+void gemm_tf32_v1_configure(const Plan& p, GemmDev& g);  // round-1 kernel (gemm_tf32_v1.cu), CTN_TF32_V1=1
+cudaError_t launch_gemm_tf32_v1(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);
 size_t gemm_scratch_bytes(const GemmDev& g);
 cudaError_t launch_finalize(const ExecCtx& c, const Launch& l);
 cudaError_t launch_materialize(const ExecCtx& c, const Launch& l, bool vec_ok);

@@ -102,7 +102,13 @@ struct LoweredStep {
   std::vector<std::pair<int32_t, GemmMode>> gm, gn, gk;  // unfused GEMM groups with their labels
   int32_t g_n_batch = 0;
   bool fused_consumer = false;
+  int32_t desc_step = -1;                 // contraction-list entry whose result this step writes
+  bool overridden = false;                // its output got a non-default physical layout
+  std::vector<int32_t> row_labels, col_labels, batch_labels;  // GEMM orientation of the output labels
 };
+
+// Physical layouts chosen for intermediates: contraction-list entry -> output labels, outermost first.
+typedef std::map<int32_t, std::vector<int32_t>> LayoutOverrides;
 
 static void fuse_modes(std::vector<ModeDev>& modes, int n_in, bool out_modes) {
   // drop extent-1 modes, then merge neighbours (outer, inner) whenever
@@ -182,7 +188,8 @@ static void prefer_unit_stride_innermost(GemmMode* grp, int n, const GemmMode* k
   }
 }
 
-static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& live, LoweredStep& ls) {
+static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& live, LoweredStep& ls,
+                      const std::vector<int32_t>* phys_order) {
   if (sd.n_inputs < 1 || !sd.positions || !sd.input_ranks) return CTN_ERR_INVALID;
   // pop operands exactly like `[operands.pop(x) for x in inds]` (einsum.py:344)
   for (int i = 0; i < sd.n_inputs; ++i) {
@@ -228,6 +235,20 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
   }
   out.strides.assign(sd.out_rank, 1);
   for (int a = sd.out_rank - 2; a >= 0; --a) out.strides[a] = out.strides[a + 1] * out.extents[a + 1];
+  if (phys_order && (int)phys_order->size() == sd.out_rank) {
+    // an intermediate may live in any dense layout (nobody but the plan's own kernels reads it):
+    // `phys_order` lists its labels outermost first
+    int64_t st = 1;
+    bool ok = true;
+    std::vector<int64_t> strides(sd.out_rank, 0);
+    for (int a = sd.out_rank - 1; a >= 0 && ok; --a) {
+      auto it = std::find(out.labels.begin(), out.labels.end(), (*phys_order)[a]);
+      if (it == out.labels.end() || strides[it - out.labels.begin()] != 0) { ok = false; break; }
+      strides[it - out.labels.begin()] = st;
+      st *= out.extents[it - out.labels.begin()];
+    }
+    if (ok) { out.strides = strides; ls.overridden = true; }
+  }
   for (auto e : out.extents) out.numel *= e;
   ls.out_slot = (int32_t)p.slots.size();
   p.slots.push_back(out);
@@ -264,7 +285,7 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
   }
   // same-layout Hadamard product?  every label in the output, every input
   // carrying all output labels in output order with identical (contiguous) strides
-  ls.elementwise = !any_sum;
+  ls.elementwise = !any_sum && !ls.overridden;
   if (ls.elementwise) {
     for (int i = 0; i < n_in && ls.elementwise; ++i) {
       const Slot& s = p.slots[ls.in_slots[i]];
@@ -286,9 +307,8 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
       if (n >= kGemmMaxModes) { ok = false; return; }
       grp[n++] = m;
     };
-    int64_t sc = 1;
     std::map<int32_t, int64_t> c_stride;
-    for (int a = sd.out_rank - 1; a >= 0; --a) { c_stride[sd.out_labels[a]] = sc; sc *= out.extents[a]; }
+    for (int a = 0; a < sd.out_rank; ++a) c_stride[sd.out_labels[a]] = p.slots[ls.out_slot].strides[a];
     auto stride_of = [&](int i, int32_t l) -> int64_t {
       auto it = in_stride[i].find(l);
       return (it == in_stride[i].end() || in_extent[i][l] != extent[l]) ? 0 : it->second;
@@ -298,9 +318,9 @@ static int lower_step(Plan& p, const ctn_step_desc& sd, std::vector<int32_t>& li
       int32_t l = sd.out_labels[a];
       bool inA = in_stride[0].count(l) > 0, inB = in_stride[1].count(l) > 0;
       GemmMode m{extent[l], stride_of(0, l), stride_of(1, l), c_stride[l], 0};
-      if (inA && inB) { push(g.batch, g.n_batch, m); ls.g_n_batch++; }
-      else if (inA) { push(g.m, g.n_m, m); ls.gm.emplace_back(l, m); }
-      else { push(g.n, g.n_n, m); ls.gn.emplace_back(l, m); }
+      if (inA && inB) { push(g.batch, g.n_batch, m); ls.g_n_batch++; ls.batch_labels.push_back(l); }
+      else if (inA) { push(g.m, g.n_m, m); ls.gm.emplace_back(l, m); ls.row_labels.push_back(l); }
+      else { push(g.n, g.n_n, m); ls.gn.emplace_back(l, m); ls.col_labels.push_back(l); }
     }
     for (auto& kv : extent) {
       if (out_set.count(kv.first)) continue;
@@ -410,6 +430,13 @@ static bool try_fuse_consumer(Plan& p, LoweredStep& cur, const LoweredStep& nxt)
   g.fuse_sb = rmode->sb;
   g.fuse_sw = sw[r];
   // merge
+  cur.row_labels.clear();
+  cur.col_labels.clear();
+  cur.batch_labels.clear();
+  for (auto& kv : gm) cur.row_labels.push_back(kv.first);
+  for (auto& kv : gn) if (kv.first != r) cur.col_labels.push_back(kv.first);
+  cur.desc_step = nxt.desc_step;
+  cur.overridden = nxt.overridden;
   cur.in_slots = ab;
   cur.in_slots.push_back(nxt.in_slots[wi]);
   cur.out_slot = nxt.out_slot;
@@ -435,7 +462,13 @@ static void layout_state(Plan& p) {
   s.total = align_up(off, 256);
 }
 
-static int build_plan(const ctn_plan_desc& d, Plan& p) {
+// One compilation pass.  `ov` (may be null) fixes the physical layout of some intermediates; `want`
+// (may be null) receives the layouts this pass would like to see in a second pass: row-index-fastest
+// ("M-fast") results for the tcgen05 kernel, whose accumulator rows live in TMEM lanes = threads, so
+// that its epilogue stores and the next step's A-operand loads are coalesced with no transposition.
+// `violated` is set when a step whose output layout was overridden did not end up on that kernel
+// (the other kernels write their output flat in label order): the caller then keeps the first pass.
+static int build_plan(const ctn_plan_desc& d, Plan& p, const LayoutOverrides* ov, LayoutOverrides* want, bool* violated) {
   if (d.abi_version != CTN_ABI_VERSION) return CTN_ERR_INVALID;
   if (d.dtype != CTN_F32 && d.dtype != CTN_F64) return CTN_ERR_UNSUPPORTED;
   if (d.n_operands < 1 || d.n_steps < 1 || !d.operand_ranks || !d.steps) return CTN_ERR_INVALID;
@@ -475,7 +508,13 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
   const bool fuse = !(d.flags & CTN_PLAN_EXACT_STEPS);
   for (int t = 0; t < d.n_steps; ++t) {
     LoweredStep ls;
-    int rc = lower_step(p, d.steps[t], live, ls);
+    ls.desc_step = t;
+    const std::vector<int32_t>* phys = nullptr;
+    if (ov && t + 1 < d.n_steps) {
+      auto it = ov->find(t);
+      if (it != ov->end()) phys = &it->second;
+    }
+    int rc = lower_step(p, d.steps[t], live, ls, phys);
     if (rc != CTN_OK) return rc;
     if (p.slots[ls.out_slot].numel == 0) return CTN_ERR_UNSUPPORTED;  // empty tensors
     p.flops += ls.flops;
@@ -489,6 +528,7 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
         for (auto s : ls.in_slots)
           if (s != prev.out_slot) prev.in_slots.push_back(s);
         prev.out_slot = ls.out_slot;
+        prev.desc_step = ls.desc_step;
         prev.flops += ls.flops;
         continue;
       }
@@ -509,6 +549,8 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
   std::vector<std::pair<size_t, size_t>> deferred;  // buffers read inside the current interpreter launch
   const bool allow_interp = !(d.flags & CTN_PLAN_NO_INTERPRETER);
   const bool allow_gemm = !(d.flags & CTN_PLAN_NO_GEMM);
+  static const bool tf32_v1 = getenv("CTN_TF32_V1") != nullptr;        // round-1 kernel (A/B comparisons)
+  static const bool no_mfast = getenv("CTN_TF32_NO_MFAST") != nullptr;  // keep label-order intermediates
   for (size_t t = 0; t < lowered.size(); ++t) {
     LoweredStep& ls = lowered[t];
     StepDev sd{};
@@ -535,7 +577,8 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
         sd.gemm_off = (int32_t)p.gemms.size();
         const int32_t pr = ls.gemm.fuse_pr;
         const int64_t fsb = ls.gemm.fuse_sb, fsw = ls.gemm.fuse_sw;
-        gemm_tf32_configure(p, ls.gemm);
+        if (tf32_v1) gemm_tf32_v1_configure(p, ls.gemm);
+        else gemm_tf32_configure(p, ls.gemm);
         ls.gemm.fuse_pr = pr; ls.gemm.fuse_sb = fsb; ls.gemm.fuse_sw = fsw;
         if (fsb & 3) ls.gemm.lb = 2;  // r-stride breaks 16-byte alignment of B chunks: element-wise staging
         p.gemms.push_back(ls.gemm);
@@ -573,9 +616,21 @@ static int build_plan(const ctn_plan_desc& d, Plan& p) {
         } else if (gemm_tf32_supported(p, sd, ls.gemm)) {
           sd.kind = kGemm;
           sd.gemm_off = (int32_t)p.gemms.size();
-          gemm_tf32_configure(p, ls.gemm);
+          if (tf32_v1) gemm_tf32_v1_configure(p, ls.gemm);
+          else gemm_tf32_configure(p, ls.gemm);
           p.gemms.push_back(ls.gemm);
         }
+      }
+    }
+    {
+      const bool on_tc = sd.kind == kGemm && p.dtype == CTN_F32 && p.gemms[sd.gemm_off].cfg == 8;
+      if (ls.overridden && !on_tc && violated) *violated = true;
+      if (want && on_tc && !no_mfast && !sd.is_final && !ls.row_labels.empty() && p.gemms[sd.gemm_off].M >= 32) {
+        std::vector<int32_t> order = ls.batch_labels;
+        order.insert(order.end(), ls.col_labels.begin(), ls.col_labels.end());
+        order.insert(order.end(), ls.row_labels.begin(), ls.row_labels.end());
+        if (order.size() == p.slots[ls.out_slot].labels.size() && order != p.slots[ls.out_slot].labels)
+          (*want)[ls.desc_step] = order;
       }
     }
     // place the output, then release the inputs (never alias within a step)
@@ -784,6 +839,7 @@ const char* ctn_status_string(int status) {
     case CTN_ERR_CUDA: return "CUDA error";
     case CTN_ERR_NOMEM: return "out of memory";
     case CTN_ERR_NO_DEVICE: return "no sm_100 CUDA device available";
+    case CTN_ERR_INTERNAL: return "internal kernel error (pipeline time-out)";
     default: return "unknown status";
   }
 }
@@ -797,7 +853,19 @@ int ctn_plan_create(const ctn_plan_desc* desc, ctn_plan** plan_out) {
   int rc;
   try {
     rc = query_device(h->p);
-    if (rc == CTN_OK) rc = build_plan(*desc, h->p);
+    LayoutOverrides want;
+    if (rc == CTN_OK) rc = build_plan(*desc, h->p, nullptr, &want, nullptr);
+    if (rc == CTN_OK && !want.empty()) {
+      // second pass with the layouts the tensor-core steps asked for
+      ctn_plan* h2 = new (std::nothrow) ctn_plan();
+      if (h2) {
+        bool violated = false;
+        int rc2 = query_device(h2->p);
+        if (rc2 == CTN_OK) rc2 = build_plan(*desc, h2->p, &want, nullptr, &violated);
+        if (rc2 == CTN_OK && !violated) std::swap(h, h2);
+        ctn_plan_destroy(h2);
+      }
+    }
     if (rc == CTN_OK) rc = upload_plan(h->p);
   } catch (const std::bad_alloc&) {
     rc = CTN_ERR_NOMEM;
@@ -869,6 +937,37 @@ double ctn_plan_step_bytes(const ctn_plan* plan) {
   return b;
 }
 
+int ctn_plan_describe(const ctn_plan* plan, char* buf, size_t n) {
+  if (!plan || !buf || n == 0) return CTN_ERR_INVALID;
+  const Plan& p = plan->p;
+  std::string out;
+  char line[512];
+  for (size_t li = 0; li < p.launches.size(); ++li) {
+    const Launch& l = p.launches[li];
+    const StepDev& s = p.steps[l.first_step];
+    static const char* names[] = {"generic", "chain", "interp", "gemm", "finalize", "materialize", "gemm_reduce"};
+    snprintf(line, sizeof line, "%zu %s steps=%d..%d", li, names[l.kind], l.first_step, l.last_step);
+    out += line;
+    if (l.kind == kGemm) {
+      const GemmDev& g = p.gemms[s.gemm_off];
+      snprintf(line, sizeof line, " cfg=%d la=%d lb=%d B=%lld M=%lld N=%lld K=%lld fuse_pr=%d cvec=%d", g.cfg, g.la, g.lb,
+               (long long)g.B, (long long)g.M, (long long)g.N, (long long)g.K, g.fuse_pr, g.fuse_pad & 1);
+      out += line;
+    }
+    if (l.kind != kFinalize && l.kind != kMaterialize && l.kind != kGemmReduce && l.kind != kInterp) {
+      const Slot& o = p.slots[s.out_slot];
+      out += " out_strides=";
+      for (size_t a = 0; a < o.strides.size(); ++a) {
+        snprintf(line, sizeof line, "%s%lld", a ? "," : "", (long long)o.strides[a]);
+        out += line;
+      }
+    }
+    out += "\n";
+  }
+  snprintf(buf, n, "%s", out.c_str());
+  return CTN_OK;
+}
+
 int ctn_plan_launch_kind(const ctn_plan* plan, int i) {
   if (!plan || i < 0 || i >= (int)plan->p.launches.size()) return -1;
   return plan->p.launches[i].kind;
@@ -930,8 +1029,11 @@ static int execute_impl(const ctn_plan* plan, const void* const* operands, void*
       case kGemm: {
         const StepDev& gs = p.steps[l.first_step];
         const bool a_al = ((uintptr_t)ptrs[gs.in_slot[0]] & 15) == 0, b_al = ((uintptr_t)ptrs[gs.in_slot[1]] & 15) == 0;
-        if (p.gemms[gs.gemm_off].cfg == 3 || p.gemms[gs.gemm_off].cfg == 4) e = launch_skinny(ctx, l);
-        else e = p.dtype == CTN_F32 ? launch_gemm_tf32(ctx, l, a_al, b_al) : launch_gemm(ctx, l, a_al, b_al);
+        const int cfg = p.gemms[gs.gemm_off].cfg;
+        if (cfg == 3 || cfg == 4) e = launch_skinny(ctx, l);
+        else if (p.dtype != CTN_F32) e = launch_gemm(ctx, l, a_al, b_al);
+        else if (cfg == 8) e = launch_gemm_tf32(ctx, l, a_al, b_al, ((uintptr_t)ptrs[gs.out_slot] & 15) == 0, ptrs[gs.in_slot[1]]);
+        else e = launch_gemm_tf32_v1(ctx, l, a_al, b_al);
         break;
       }
       case kGemmReduce: e = launch_gemm_reduce(ctx, l); break;
@@ -1070,7 +1172,13 @@ int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void
   CTN_CUDA(cudaMemcpyAsync(tail, p.h_log, 16, cudaMemcpyDeviceToHost, 0));
   CTN_CUDA(cudaStreamSynchronize(0));
   *log_scale_host = tail[0];
-  if (flags_host) memcpy(flags_host, &tail[1], sizeof(int32_t));
+  int32_t fl = 0;
+  memcpy(&fl, &tail[1], sizeof(int32_t));
+  if (flags_host) *flags_host = fl;
+  if (fl & CTN_RESULT_INTERNAL) {
+    g_cuda_error = "a kernel's internal pipeline timed out (StateHdr diagnostics lost); result invalid";
+    return CTN_ERR_INTERNAL;
+  }
   return CTN_OK;
 }
 

@@ -41,7 +41,7 @@ EXPORTS = (
     "ctn_plan_create", "ctn_plan_destroy", "ctn_plan_workspace_bytes",
     "ctn_plan_output_rank", "ctn_plan_output_extents", "ctn_plan_output_numel",
     "ctn_plan_num_launches", "ctn_plan_flops", "ctn_plan_step_bytes",
-    "ctn_plan_launch_kind", "ctn_plan_execute", "ctn_plan_execute_timed", "ctn_plan_execute_host",
+    "ctn_plan_launch_kind", "ctn_plan_describe", "ctn_plan_execute", "ctn_plan_execute_timed", "ctn_plan_execute_host",
     "ctn_shard_stats", "ctn_merge_batch_shards", "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
 )
 
@@ -113,6 +113,8 @@ def load_library():
         lib.ctn_plan_step_bytes.restype = dbl
         lib.ctn_plan_launch_kind.argtypes = [vp, ctypes.c_int]
         lib.ctn_plan_launch_kind.restype = ctypes.c_int
+        lib.ctn_plan_describe.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
+        lib.ctn_plan_describe.restype = ctypes.c_int
         lib.ctn_plan_execute.argtypes = [vp, ctypes.POINTER(vp), vp, vp, vp, vp, ctypes.c_int, vp]
         lib.ctn_plan_execute.restype = ctypes.c_int
         lib.ctn_plan_execute_timed.argtypes = [vp, ctypes.POINTER(vp), vp, vp, vp, vp, ctypes.c_int, vp,
@@ -295,6 +297,12 @@ class Plan:
                 "ctn_plan_execute",
             )
             return out, tail
+
+    def describe(self):
+        """What the plan compiler decided: one line per launch."""
+        buf = ctypes.create_string_buffer(1 << 20)
+        _check(self._lib.ctn_plan_describe(self._h, buf, len(buf)), "ctn_plan_describe")
+        return buf.value.decode()
 
     @property
     def may_degenerate(self):

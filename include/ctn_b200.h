@@ -49,7 +49,8 @@ enum {
   CTN_ERR_UNSUPPORTED = 3, /* valid but outside what the kernels handle         */
   CTN_ERR_CUDA = 4,        /* a CUDA runtime call failed; see ctn_last_cuda_error */
   CTN_ERR_NOMEM = 5,
-  CTN_ERR_NO_DEVICE = 6    /* no sm_100 device visible                          */
+  CTN_ERR_NO_DEVICE = 6,   /* no sm_100 device visible                          */
+  CTN_ERR_INTERNAL = 7     /* a kernel gave up waiting on its own pipeline (bug) */
 };
 
 /* arithmetic type of the whole plan */
@@ -78,9 +79,12 @@ enum {
 
 /* result flags written next to the log-scale */
 enum {
-  CTN_RESULT_DEGENERATE = 1 /* a fused step met a norm <= 1e-7 or a non-finite
-                               value: re-run with CTN_PLAN_EXACT_STEPS to get
-                               the reference's exact (tensor, log-scale) pair */
+  CTN_RESULT_DEGENERATE = 1, /* a fused step met a norm <= 1e-7 or a non-finite
+                                value: re-run with CTN_PLAN_EXACT_STEPS to get
+                                the reference's exact (tensor, log-scale) pair */
+  CTN_RESULT_INTERNAL = 2    /* a kernel's bounded pipeline wait expired: the result
+                                is invalid (ctn_plan_execute_host returns
+                                CTN_ERR_INTERNAL; device-path callers must test it) */
 };
 
 /* One entry of the contraction list (contractn/einsum.py:341-344): the
@@ -133,6 +137,9 @@ double ctn_plan_step_bytes(const ctn_plan* plan);     /* sum over launches of op
 /* kind of launch i: 0 generic, 1 hadamard-chain, 2 interpreter, 3 gemm, 4 finalize,
  * 5 chain materialise pass, 6 split-K reduce pass; -1 past the end */
 int ctn_plan_launch_kind(const ctn_plan* plan, int i);
+/* One text line per launch (kernel class, GEMM view, tile configuration, physical strides of the
+ * result) into buf[0..n): what the plan compiler decided, for tests and reports. */
+int ctn_plan_describe(const ctn_plan* plan, char* buf, size_t n);
 
 /* Run the plan: the body of _core_contract (contractn/einsum.py:341-393) plus
  * stabilize after every step (einsum.py:387, 89-107) and, for CTN_OUT_DENSE,
