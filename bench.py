@@ -1,22 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the TN.contract() hot path on B200 (contract in the task brief).
 
-Workload (BASELINE.json configs[1], SURVEY.md section 8d cfg 2): an order-101
-copy-node hub with 100 attached (2, B) float64 tensors, B = 2^20 batched
-evaluations -- einsum "ab,ab,...,ab->ab", 99 pairwise Hadamard steps each
-followed by ``stabilize`` in the reference; ONE fused n-ary kernel here.
+Headline workload (BASELINE.json configs[1], SURVEY.md section 8d cfg 2): an order-101
+copy-node hub with 100 attached (2, B) float64 tensors, B = 2^20 batched evaluations --
+einsum "ab,ab,...,ab->ab", 99 pairwise Hadamard steps each followed by ``stabilize`` in
+the reference; ONE fused n-ary kernel here.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--configs LIST|none]
 
-One JSON line on stdout (rank 0).  ``value`` = contractions/s with the operands
-resident in HBM; ``e2e`` = the same through the public API
-(``TN.make_contract_fun`` -> ``contract`` -> ``ctn_plan_execute_host``) with
-pinned HOST buffers, H2D/D2H inside the timed region.  N > 1: one process per
-GPU, the batch is sharded (weak scaling: B evaluations per GPU), the shards'
-(mantissa, log-scale) pairs are merged to one global scale after a 24-byte NCCL all-gather.
+One JSON line on stdout (rank 0).  ``value`` = contractions/s with the operands resident
+in HBM; ``e2e`` = the same through the public API (``TN.make_contract_fun`` ->
+``contract`` -> ``ctn_plan_execute_host``) with pinned HOST buffers, H2D/D2H inside the
+timed region.  ``configs`` (N = 1 only) carries one record per other BASELINE
+configuration -- cfg 1 (README chain), cfg 3 literal (batched MPS, float32, the tcgen05
+kernel), cfg 4 tier M CP + Tucker (FP64 DMMA), cfg 5 at its parity tier 8x8 D=8 -- each
+with its own roofline, end-to-end number, CPU baseline (the oracle port) and errors
+against the float64 oracle on the same inputs.  ``peaks`` are the denominators: HBM from
+MEASURED_PEAKS.json, FP64 and TF32 GEMM measured HERE with cuBLAS (torch.matmul 8192^3).
+N > 1: one process per GPU, the batch is sharded (weak scaling: B evaluations per GPU),
+the shards' (mantissa, log-scale) pairs are merged to one global scale on the device.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -32,6 +38,7 @@ if ROOT not in sys.path:
 N_VEC = 100
 BATCH = 1 << 20
 METRIC = "contractions/s (cfg2: order-101 copy hub x 100 (2,B) f64, B=2^20 batched evaluations per GPU)"
+DEFAULT_CONFIGS = "cfg1,cfg3,cfg4m,cfg4t,cfg5"
 
 
 def parse_args():
@@ -42,27 +49,19 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="evaluations per GPU (default 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default=DEFAULT_CONFIGS,
+                    help="other BASELINE configurations to measure at N=1 (comma list or 'none')")
     return ap.parse_args()
 
 
-def ncu_traffic_bytes():
-    """DRAM bytes per chain-kernel launch from the committed `ncu --set full`
-    capture of this same command (profiles/r1_cfg2_chain_kernel_raw.csv)."""
-    import csv
+def headline_config(batch, world):
+    """The `config` object of the JSON line: identical for both arms by construction."""
+    from contractn_b200 import planner
 
-    path = os.path.join(ROOT, "profiles", "r1_cfg2_chain_kernel_raw.csv")
-    try:
-        with open(path) as f:
-            rows = list(csv.reader(f))
-        hdr, units, vals = rows[0], rows[1], rows[2]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        total = 0.0
-        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            i = hdr.index(name)
-            total += float(vals[i].replace(",", "")) * scale[units[i]]
-        return total
-    except Exception:
-        return None
+    return {"workload": "cfg2 hub-101 x (2,B) f64", "batch_per_gpu": batch, "n_operands": N_VEC,
+            "einsum": "ab x100 -> ab", "pairwise_steps": N_VEC - 1, "planner": planner.planner_name(),
+            "l2": "inputs (1.68 GB) exceed L2 (126 MB); no flush needed",
+            "parallelism": f"batch-shard x{world}" if world > 1 else "single GPU"}
 
 
 def measured_peaks():
@@ -72,6 +71,38 @@ def measured_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cublas_peaks():
+    """FP64 and TF32 GEMM throughput of this GPU, measured now with cuBLAS (torch.matmul, 8192^3,
+    best of 5 after warm-up): the denominators of the tensor-bound rooflines below."""
+    import torch
+
+    out = {}
+    n = 8192
+    for name, dt, tf32 in (("f64_tflops", torch.float64, False), ("tf32_tflops", torch.float32, True)):
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        a = torch.rand(n, n, dtype=dt, device="cuda")
+        b = torch.rand(n, n, dtype=dt, device="cuda")
+        c = torch.empty(n, n, dtype=dt, device="cuda")
+        for _ in range(2):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[name] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b, c
+    torch.cuda.empty_cache()
+    out["how"] = "torch.matmul 8192^3 (cuBLAS), best of 5, CUDA events, measured in this run"
+    return out
 
 
 class ClockSampler:
@@ -130,18 +161,6 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_network(TN, arrays):
-    """cfg 2: hub `a` first, batch hub `b`, then the dense (2, B) nodes."""
-    tn = TN()
-    hub = tn.add_copy_node(len(arrays) + 1)
-    hub_b = tn.add_copy_node(len(arrays) + 1)
-    for i, arr in enumerate(arrays):
-        node = tn.add_dense_node(arr)
-        tn.connect_nodes(hub, node, i, 0)
-        tn.connect_nodes(hub_b, node, i, 1)
-    return tn
-
-
 def host_operands(batch, seed, pinned):
     rng = np.random.default_rng(seed)
     out = []
@@ -157,19 +176,6 @@ def host_operands(batch, seed, pinned):
     return [(None, rng.uniform(0.9, 1.1, (2, batch))) for _ in range(N_VEC)]
 
 
-def cpu_reference_time(arrays, contraction_list, reps):
-    """The oracle port (numpy restatement of _core_contract + stabilize) on the
-    host cores; best of `reps`."""
-    from oracle import contract_oracle as oracle
-
-    best = float("inf")
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        oracle.core_contract(arrays, contraction_list)
-        best = min(best, time.perf_counter() - t0)
-    return best
-
-
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -180,29 +186,39 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def oracle_contract_fun(einstr, shapes, optimize):
+    """The reference's ``contract_fun`` (ctn.py:378-385) restated on the oracle: arg packing is the
+    identity here, then ``contract`` = cached path lookup + ``_core_contract`` + split output."""
+    from contractn_b200 import planner
+    from oracle import contract_oracle as oracle
+
+    def fun(arrays):
+        lst = planner.cached_contract_list(einstr, shapes, optimize=optimize)  # lru, like einsum.py:313
+        return oracle.core_contract(arrays, lst)
+
+    return fun
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm (numpy port, oracle/) on the host."""
+    """--impl reference: the reference algorithm (numpy port, oracle/) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from contractn_b200 import planner
-
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     batch = args.batch
-    # ~3 s per full-size contraction on 8 cores: shrink the sample if K+W is large
+    # ~1 s per full-size contraction on the host: shrink the sample if K + W is large
     total = args.steps + args.warmup
     sample = batch
-    while sample > 1 << 14 and total * 3.0 * sample / BATCH > 150.0:
+    while sample > 1 << 14 and total * 1.2 * sample / BATCH > 150.0:
         sample //= 2
     arrays = [a for _, a in host_operands(sample, 1002, pinned=False)]
     einstr = ",".join(["ab"] * N_VEC) + "->ab"
-    lst = planner.contract_path(einstr, *[a.shape for a in arrays])[1]
-    from oracle import contract_oracle as oracle
-
+    fun = oracle_contract_fun(einstr, tuple(a.shape for a in arrays), "auto")
     for _ in range(args.warmup):
-        oracle.core_contract(arrays, lst)
+        fun(arrays)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.core_contract(arrays, lst)
+        fun(arrays)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = (sample / batch) / dt
     line = {
@@ -210,14 +226,161 @@ def run_reference(args):
         "metric": METRIC, "value": value, "unit": "contractions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2 hub-101 x (2,B) f64", "batch_per_gpu": batch, "n_operands": N_VEC,
-                   "planner": planner.planner_name()},
+        "config": headline_config(batch, world),
         "cpu_baseline": {"value": value, "unit": "contractions/s", "cores": host_threads(), "kind": "port",
-                         "sample": f"batch {sample} of {batch} per step, scaled linearly; numpy einsum steps are single-threaded"},
+                         "sample": f"batch {sample} of {batch} per step, scaled linearly; contract_fun-equivalent "
+                                   "(cached path lookup + executor); numpy einsum steps are single-threaded"},
         "e2e": {"value": value, "unit": "contractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# the other BASELINE configurations (N = 1)
+# ---------------------------------------------------------------------------
+def _time_device(plan, dev_ops, steps):
+    import torch
+
+    for _ in range(3):
+        plan.execute_device(dev_ops)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out, tail = plan.execute_device(dev_ops)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    per = np.zeros(plan.num_launches)
+    reps = 3
+    for _ in range(reps):
+        _, _, kms = plan.execute_device(dev_ops, timed=True)
+        per += np.array(kms)
+    return ms, per / reps, out, tail
+
+
+def run_config(name, peaks, hbm_peak, with_cpu):
+    """One record of the `configs` array."""
+    import torch
+
+    from contractn_b200 import engine, networks, planner
+    from oracle import contract_oracle as oracle
+
+    spec = {
+        "cfg1": ("cfg1 README chain: vector + 1000 x (3,3), f64", lambda: networks.chain_tn(1000), 20),
+        "cfg3": ("cfg3 batched MPS: 512 sites, bond 512, phys 2, batch 4096, f32, explicit sweep path (literal size)",
+                 lambda: networks.mps_tn(512, 512, 2, 4096), 5),
+        "cfg4m": ("cfg4 CP tier M: 3 factors (1024, 1024) on an order-3 hub, f64 (8.6 GB output)",
+                  lambda: networks.cp_tn(1024, 1024), 3),
+        "cfg4t": ("cfg4 Tucker: core (256,256,256), factors (512, 256), f64", lambda: networks.tucker_tn(512, 256), 5),
+        "cfg5": ("cfg5 PEPS parity tier: closed 8x8 grid, D = 8, f64, row-by-row sweep path (6.5e11 FLOP)",
+                 lambda: networks.peps_tn(8, 8), 5),
+    }[name]
+    title, build, steps = spec
+    tn, optimize = build()
+    einstr = tn.einsum_str
+    params = tn.params
+    shapes = tuple(tuple(p.shape) for p in params)
+    dtype = params[0].dtype
+    lst = planner.cached_contract_list(einstr, shapes, optimize=optimize)
+    plan = engine.get_plan(lst, shapes, dtype, strides=tuple(engine._elem_strides(p) for p in params),
+                           device=torch.cuda.current_device())
+    dev_ops = [torch.as_tensor(p).cuda() for p in params]
+    ms, per, out, tail = _time_device(plan, dev_ops, steps)
+    kinds = plan.launch_kinds
+    by_kind = {}
+    for k, t in zip(kinds, per):
+        by_kind[k] = by_kind.get(k, 0.0) + float(t)
+    rec = {"name": name, "workload": title, "dtype": "f32" if dtype == np.float32 else "f64",
+           "pairwise_steps": len(lst), "kernels_per_contraction": plan.num_launches,
+           "ms_per_contraction": ms, "contractions_per_s": 1e3 / ms, "path_flops": plan.flops,
+           "path_tflops": plan.flops / ms / 1e9, "algorithmic_GBps": plan.step_bytes / ms / 1e6,
+           "ms_by_kernel_class": by_kind, "workspace_MB": plan.workspace_bytes / 1e6}
+
+    # ---- roofline of the dominant kernel class ----
+    if name == "cfg1":
+        rec["roofline"] = {"bound": "latency", "kernel": "interp_kernel (one launch, 1000 dependent steps)",
+                           "us_per_dependent_step": ms * 1e3 / len(lst), "achieved": None, "peak": None, "frac": None,
+                           "unit": None, "traffic": None}
+    else:
+        gemm_ms = by_kind.get("gemm", 0.0)
+        # FLOPs of the GEMM-class launches = the plan's path FLOPs minus the (few) non-GEMM steps; for these
+        # configurations the GEMM steps carry > 99.9 % of the path FLOPs, so the plan total is used
+        if dtype == np.float32:
+            peak, unit_name = peaks["tf32_tflops"] / 3.0, "gemm_tf32x3_kernel (tcgen05 kind::tf32, 3 MMAs per product)"
+            src = "cuBLAS TF32 8192^3 measured in this run, divided by 3 (error-compensated split)"
+        else:
+            peak, unit_name = peaks["f64_tflops"], "gemm_f64_kernel / skinny_dmma_kernel (DMMA)"
+            src = "cuBLAS DGEMM 8192^3 measured in this run"
+        ach = plan.flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        rec["roofline"] = {"bound": "tensor", "kernel": unit_name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                           "frac": ach / peak if ach else None, "traffic": None, "kernel_ms": gemm_ms,
+                           "share_of_step": gemm_ms / float(per.sum()) if per.sum() > 0 else None, "peak_source": src}
+
+    # ---- end to end through the public API on host arrays ----
+    try:
+        contract_fun = tn.make_contract_fun(optimize=optimize, split_format=True)
+        contract_fun(params, ())
+        n_e2e = 1 if name == "cfg4m" else 3
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            T_h, c_h = contract_fun(params, ())
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        rec["e2e"] = {"value": 1.0 / e2e_s, "unit": "contractions/s", "ms_per_step": e2e_s * 1e3,
+                      "h2d_bytes_per_step": int(sum(p.nbytes for p in params)),
+                      "d2h_bytes_per_step": int(np.asarray(T_h).nbytes + 16), "steps": n_e2e,
+                      "api": "TN.make_contract_fun()(params, inputs) on host numpy arrays"}
+        del T_h
+    except MemoryError as exc:  # the 8.6 GB host result of cfg4m on a small-memory box
+        rec["e2e"] = {"value": None, "error": str(exc)}
+
+    # ---- errors against the float64 oracle on the same inputs, and the CPU baseline ----
+    c_gpu = float(tail[0].item())
+    if name == "cfg4m":
+        # the oracle needs minutes and 17 GB here: check 4000 sampled entries against the defining sum
+        rng = np.random.default_rng(4)
+        idx = rng.integers(0, 1024, size=(4000, 3))
+        got = out[idx[:, 0], idx[:, 1], idx[:, 2]].cpu().numpy() * math.exp(c_gpu)
+        f1, f2, f3 = params
+        want = np.einsum("na,na,na->n", f1[idx[:, 0]], f2[idx[:, 1]], f3[idx[:, 2]])
+        rec["errors"] = {"max_rel_err_sampled_entries": float(np.abs(got / want - 1).max()), "samples": 4000,
+                         "mean_abs_T_minus_1": abs(float(out.abs().mean().item()) - 1.0),
+                         "vs": "defining sum on sampled entries (float64) + canonical form mean|T| = 1"}
+        if with_cpu:
+            tn_s, opt_s = networks.cp_tn(256, 256)
+            ps = tn_s.params
+            fun = oracle_contract_fun(tn_s.einsum_str, tuple(p.shape for p in ps), opt_s)
+            fun(ps)
+            t0 = time.perf_counter()
+            fun(ps)
+            sec = time.perf_counter() - t0
+            scale = (1024 / 256) ** 3 * (1024 / 256)  # I^3 * R work
+            rec["cpu_baseline"] = {"value": 1.0 / (sec * scale), "unit": "contractions/s", "cores": host_threads(),
+                                   "kind": "port", "sample": f"tier S (I = R = 256) in {sec:.3f} s, scaled by I^3 R = {scale:.0f}x"}
+    else:
+        ops64 = [np.asarray(p, dtype=np.float64) for p in params]
+        t0 = time.perf_counter()
+        T0, c0 = oracle.core_contract(ops64, lst)
+        sec64 = time.perf_counter() - t0
+        T = out.cpu().numpy().astype(np.float64)
+        T0 = np.asarray(T0, dtype=np.float64)
+        rec["errors"] = {"max_rel_err_T": float(np.abs(T - T0).max() / (np.abs(T0).max() or 1.0)),
+                         "abs_err_log_scale": abs(c_gpu - float(c0)), "vs": "oracle in float64 on the same inputs"}
+        if with_cpu:
+            if dtype == np.float64:
+                sec, how = sec64, "full workload, one contraction (the float64 oracle run used for the errors)"
+            else:
+                fun = oracle_contract_fun(einstr, shapes, optimize)
+                t0 = time.perf_counter()
+                fun(params)
+                sec, how = time.perf_counter() - t0, "full workload in float32 (the reference's arithmetic), one contraction"
+            rec["cpu_baseline"] = {"value": 1.0 / sec, "unit": "contractions/s", "cores": host_threads(), "kind": "port",
+                                   "sample": how, "seconds_per_contraction": sec}
+    del dev_ops, out
+    torch.cuda.empty_cache()
+    return rec
 
 
 def main():
@@ -228,7 +391,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from contractn_b200 import TN, engine, planner
+    from contractn_b200 import engine, networks, planner
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -244,12 +407,13 @@ def main():
     batch = args.batch
     ops = host_operands(batch, 1002 + rank, pinned=True)
     arrays = [a for _, a in ops]
-    tn = build_network(TN, arrays)
+    tn, _ = networks.hub_tn(N_VEC, batch, arrays=arrays)
     einstr = tn.einsum_str
     contract_fun = tn.make_contract_fun(optimize="auto", split_format=True)
     shapes = tuple(a.shape for a in arrays)
     lst = planner.cached_contract_list(einstr, shapes, optimize="auto")
-    plan = engine.get_plan(lst, shapes, np.float64, strides=tuple(engine._elem_strides(a) for a in arrays))
+    plan = engine.get_plan(lst, shapes, np.float64, strides=tuple(engine._elem_strides(a) for a in arrays),
+                           device=local)
     dev_ops = [t.to(dev, non_blocking=True) for t, _ in ops]
     torch.cuda.synchronize()
 
@@ -276,7 +440,7 @@ def main():
         t_wait = time.perf_counter()
         while sampler.proc is not None and not sampler.lines and time.perf_counter() - t_wait < 3.0:
             time.sleep(0.02)
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, args.warmup) + (20 if world > 1 else 0)):  # (the merge path warms up its peer exchange)
         step_device()
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -332,29 +496,46 @@ def main():
             "metric": METRIC, "value": value, "unit": "contractions/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2 hub-101 x (2,B) f64", "batch_per_gpu": batch, "n_operands": N_VEC,
-                       "einsum": "ab x100 -> ab", "pairwise_steps": len(lst), "planner": planner.planner_name(),
-                       "l2": "inputs (1.68 GB) exceed L2 (126 MB); no flush needed",
-                       "parallelism": f"batch-shard x{world}" if world > 1 else "single GPU"},
-            "path_tflops": plan.flops * value / world * world / 1e12,
+            "config": headline_config(batch, world),
+            "path_tflops": plan.flops * value / 1e12,
             "evaluations_per_s": value * batch,
             "kernels": {kind: float(per_kernel[i]) for i, kind in enumerate(kinds)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": ncu_traffic_bytes(),
+                         "frac": achieved / hbm_peak, "traffic": None,
                          "kernel": "chain_kernel<double,true,true>",
-                         "algorithmic_bytes": algo_bytes, "kernel_ms": chain_ms, "peak_source": peak_src},
+                         "algorithmic_bytes": algo_bytes, "kernel_ms": chain_ms, "peak_source": peak_src,
+                         "traffic_note": "dram bytes per launch from `ncu --set full`: profiles/ (not re-measured in this run)"},
             "e2e": {"value": e2e_value, "unit": "contractions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                    "h2d_GBps_per_gpu": h2d / e2e_s / 1e9,
                     "api": "TN.make_contract_fun()(params, inputs) on pinned numpy arrays"},
-            # chain + materialize + state-init kernel per step (+ shard-stats and merge kernels when sharded)
-            "gpu_launches": (plan.num_launches + 1 + (2 if world > 1 else 0)) * args.steps,
+            # chain + materialize + state-init kernel per step (+ the merge kernel when sharded)
+            "gpu_launches": (plan.num_launches + 1 + (1 if world > 1 else 0)) * args.steps,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            sec = cpu_reference_time(arrays, lst, reps=2)
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "contractions/s", "cores": host_threads(),
+            fun = oracle_contract_fun(einstr, shapes, "auto")
+            best = float("inf")
+            for _ in range(2):
+                t0 = time.perf_counter()
+                fun(arrays)
+                best = min(best, time.perf_counter() - t0)
+            line["cpu_baseline"] = {"value": 1.0 / best, "unit": "contractions/s", "cores": host_threads(),
                                     "kind": "port", "sample": "full cfg2 workload, best of 2 contractions",
-                                    "seconds_per_contraction": sec}
+                                    "seconds_per_contraction": best}
+        if world == 1 and args.configs != "none":
+            del dev_ops
+            torch.cuda.empty_cache()
+            peaks = cublas_peaks()
+            peaks["hbm_gbs"] = hbm_peak
+            line["peaks"] = peaks
+            recs = []
+            for nm in [c for c in args.configs.split(",") if c]:
+                try:
+                    recs.append(run_config(nm, peaks, hbm_peak, not args.no_cpu_baseline))
+                except Exception as exc:  # one configuration must not take the headline down with it
+                    recs.append({"name": nm, "error": f"{type(exc).__name__}: {exc}"})
+            line["configs"] = recs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

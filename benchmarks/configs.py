@@ -14,98 +14,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from contractn_b200 import TN, engine, planner  # noqa: E402
-from contractn_b200.planner import _ssa_to_linear  # noqa: E402
 
 
-def chain_tn(n=1000):
-    tn = TN()
-    prev = tn.add_dense_node(np.ones((3,)))
-    for _ in range(n):
-        m = tn.add_dense_node(np.ones((3, 3)))
-        tn.connect_nodes(prev, m, -1, 0)
-        prev = m
-    return tn, "auto"
-
-
-def hub_tn(n=100, batch=1 << 20, dtype=np.float64, seed=1002):
-    rng = np.random.default_rng(seed)
-    tn = TN()
-    hub, hubb = tn.add_copy_node(n + 1), tn.add_copy_node(n + 1)
-    for i in range(n):
-        v = tn.add_dense_node(rng.uniform(0.9, 1.1, (2, batch)).astype(dtype))
-        tn.connect_nodes(hub, v, i, 0)
-        tn.connect_nodes(hubb, v, i, 1)
-    return tn, "auto"
-
-
-def mps_tn(sites=512, bond=512, phys=2, batch=4096, dtype=np.float32, seed=1003):
-    """cfg 3: batch hub first, cores, then inputs; explicit left-to-right sweep path."""
-    rng = np.random.default_rng(seed)
-    tn = TN()
-    hubb = tn.add_copy_node(sites + 1)
-    cores = []
-    for i in range(sites):
-        shape = (phys, bond) if i in (0, sites - 1) else (phys, bond, bond)
-        cores.append(tn.add_dense_node(rng.uniform(0, 1, shape).astype(dtype)))
-    for i in range(sites - 1):
-        tn.connect_nodes(cores[i], cores[i + 1], -1, 1)
-    for i in range(sites):
-        x = tn.add_dense_node(rng.uniform(0.9, 1.1, (batch, phys)).astype(dtype))
-        tn.connect_nodes(cores[i], x, 0, 1)
-        tn.connect_nodes(hubb, x, i, 0)
-    # operands: cores 0..sites-1 then inputs sites..2*sites-1
-    ssa, nxt = [(0, sites)], 2 * sites
-    cur = nxt
-    nxt += 1
-    for i in range(1, sites - 1):
-        ssa.append((cur, i)); t = nxt; nxt += 1
-        ssa.append((t, sites + i)); cur = nxt; nxt += 1
-    ssa.append((sites - 1, 2 * sites - 1)); v = nxt; nxt += 1
-    ssa.append((cur, v))
-    return tn, tuple(_ssa_to_linear(ssa, 2 * sites))
-
-
-def cp_tn(I=1024, R=1024, dtype=np.float64, seed=1004):
-    rng = np.random.default_rng(seed)
-    tn = TN()
-    hub = tn.add_copy_node(3)
-    for i in range(3):
-        m = tn.add_dense_node(rng.uniform(0, 1, (I, R)).astype(dtype))
-        tn.connect_nodes(hub, m, i, 1)
-    return tn, "auto"
-
-
-def tucker_tn(I=1024, R=256, dtype=np.float64, seed=1004):
-    rng = np.random.default_rng(seed)
-    tn = TN()
-    core = tn.add_dense_node(rng.uniform(0, 1, (R, R, R)).astype(dtype))
-    for i in range(3):
-        m = tn.add_dense_node(rng.uniform(0, 1, (I, R)).astype(dtype))
-        tn.connect_nodes(core, m, i, 1)
-    return tn, "auto"
-
-
-def peps_tn(L=8, D=8, dtype=np.float64, seed=1005):
-    """cfg 5: closed LxL grid, leg order (up, left, down, right); row-by-row boundary sweep."""
-    rng = np.random.default_rng(seed)
-    tn = TN()
-    grid = {}
-    for r in range(L):
-        for c in range(L):
-            legs = [d for d, ok in (("u", r > 0), ("l", c > 0), ("d", r < L - 1), ("r", c < L - 1)) if ok]
-            grid[r, c] = (tn.add_dense_node(rng.uniform(0, 1, (D,) * len(legs)).astype(dtype)), legs)
-    for r in range(L):
-        for c in range(L):
-            node, legs = grid[r, c]
-            if c < L - 1:
-                o, ol = grid[r, c + 1]
-                tn.connect_nodes(node, o, legs.index("r"), ol.index("l"))
-            if r < L - 1:
-                o, ol = grid[r + 1, c]
-                tn.connect_nodes(node, o, legs.index("d"), ol.index("u"))
-    n = L * L
-    path = [(0, 1)] + [(0, n - t - 1) for t in range(1, n - 1)]
-    return tn, tuple(path)
+# network builders and sweep paths live in the package
+from contractn_b200.networks import chain_tn, hub_tn, mps_tn, cp_tn, tucker_tn, peps_tn  # noqa: E402,F401
 
 
 CONFIGS = {

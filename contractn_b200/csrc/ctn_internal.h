@@ -210,7 +210,7 @@ cudaError_t launch_skinny(const ExecCtx& c, const Launch& l);
 bool gemm_tf32_supported(const Plan& p, const StepDev& s, const GemmDev& g);
 void gemm_tf32_configure(const Plan& p, GemmDev& g);
 cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned, bool c_aligned,
-                             const void* b_ptr);
+                             const void* b_ptr, const void* a_ptr);
 void gemm_tf32_v1_configure(const Plan& p, GemmDev& g);  // round-1 kernel (gemm_tf32_v1.cu), CTN_TF32_V1=1
 cudaError_t launch_gemm_tf32_v1(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned);
 size_t gemm_scratch_bytes(const GemmDev& g);

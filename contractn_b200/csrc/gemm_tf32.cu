@@ -5,16 +5,19 @@
 // 3xTF32 error-compensated split (lo*hi + hi*lo + hi*hi, FP32 accumulation in TMEM) so that float32
 // results stay at sgemm-class accuracy (north_star: rtol 1e-5; one-pass TF32 gives 7e-5 per step).
 //
-// Warp-specialised, persistent over 128 x 128 output tiles, one CTA (13 warps) per SM:
+// Warp-specialised, persistent over 128 x 128 output tiles, one CTA (16 warps) per SM:
 //
-//   warps 0-3   A producers.  Thread r owns row r of the tile: it loads 32 k-values of its row from
-//               global memory into registers (two k-blocks in flight), forms lo = x - trunc(x) and
-//               writes hi and lo straight into TENSOR MEMORY (tcgen05.st) -- the A operand never
-//               touches shared memory; the MMAs read it from TMEM (tcgen05.mma [d], [a], b-desc).
-//   warps 8-11  B producers.  cp.async (16 B along whichever of N / K is contiguous) into the
-//               canonical UMMA swizzled layout, or ONE TMA tensor copy per k-block issued by an
-//               elected thread (cp.async.bulk.tensor, mbarrier complete_tx) when the operand view
-//               has a <= 5-D tensor map; then lo tile = x - trunc(x) (LDS -> STS), fence.proxy.async.
+//   warps 8-11  loaders + B converters.  They stage BOTH raw operand tiles in shared memory, three
+//               k-blocks ahead, with a cursor that runs across tile boundaries: A by cp.async (16 B
+//               along whichever of M / K is contiguous; completion counted on an mbarrier with
+//               cp.async.mbarrier.arrive.noinc), B by cp.async or by ONE TMA tensor copy per k-block
+//               issued by an elected thread (cp.async.bulk.tensor, mbarrier complete_tx) when the
+//               operand view has a tensor map.  Then B lo tile = x - trunc(x) (LDS -> STS),
+//               fence.proxy.async.
+//   warps 0-3   A converters.  Thread r reads row r of the raw A tile, forms lo = x - trunc(x) and
+//               writes hi and lo into TENSOR MEMORY (tcgen05.st): the MMAs read the A operand from
+//               TMEM (tcgen05.mma [d], [a], b-desc), so A costs the tensor core no shared-memory
+//               bandwidth and no lo tile is ever written for it.
 //   warp 12     one elected lane issues the 12 tcgen05.mma (128x128x8, kind::tf32) of a k-block;
 //               tcgen05.commit frees the stage / publishes the accumulator.  Owns TMEM alloc.
 //   warps 4-7   epilogue.  The accumulator is DOUBLE-BUFFERED in TMEM (2 x 128 columns), so the
@@ -22,15 +25,16 @@
 //               runs while the tensor core works on tile i+1.
 //
 // TMEM budget (512 columns): 2 accumulators x 128 + 4 A stages x (32 hi + 32 lo).
+// Shared memory: 4 x (B_hi 16 KB + B_lo 16 KB) + 4 x A_raw 16 KB + offset tables = 197 KB.
 //
 // Accumulator truncation.  The tensor core truncates (round toward zero) every time it adds into
 // its FP32 accumulator: a systematic relative bias of ~6e-8 per MMA in the chain, common to all
 // entries.  It cancels in the normalised mantissa T-hat but would land in the log-scale.  The kernel
-// MEASURES it: every A-producer thread also evaluates ONE entry of its row exactly (float64 FMAs
-// over the raw fp32 operands: its own registers x the raw B tile in shared memory), the epilogue
-// compares these 128 samples per tile with what the tensor core produced, and the last CTA adds
-// ln(sum|exact| / sum|tensor core|) to the log-scale register.  Unbiased by construction, data
-// independent, costs ~100 instructions per thread per k-block on warps that otherwise wait.
+// MEASURES it: warps 13-15 evaluate ONE entry per row for three of the four row quarters of every
+// tile (rotating) with round-to-nearest FP32 FMAs (unbiased; four independent partial sums) over the
+// raw fp32 operand tiles in shared memory; the epilogue compares these samples with
+// what the tensor core produced, and the last CTA adds ln(sum|exact| / sum|tensor core|) to the
+// log-scale register.  Unbiased by construction, data independent, off the producers' critical path.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -48,7 +52,7 @@ namespace t32 {
 constexpr int BM = 128, BN = 128, BKF = 32;  // BKF floats = 128 bytes = one swizzle row
 constexpr int kStages = 4;
 constexpr int kRoleThreads = 128;
-constexpr int kThreadsT = 3 * kRoleThreads + 32;  // A producers, epilogue, B producers, MMA warp
+constexpr int kThreadsT = 4 * kRoleThreads;       // A converters, epilogue, loaders, MMA warp + 3 sampler warps
 constexpr int SUB_BYTES = BN * BKF * 4;           // 16 KB: B_hi or B_lo of one stage
 constexpr int STAGE_BYTES = 2 * SUB_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
@@ -57,16 +61,28 @@ constexpr uint32_t kAStageCol0 = 256;  // A stages: 64 columns each (hi 32 | lo 
 
 // mbarrier indices
 constexpr int kFullA = 0, kFullB = kFullA + kStages, kEmpty = kFullB + kStages, kTmaFull = kEmpty + kStages,
-              kAccFull = kTmaFull + kStages, kAccEmpty = kAccFull + 2, kSmpFull = kAccEmpty + 2,
+              kARaw = kTmaFull + kStages, kARawFree = kARaw + kStages, kAccFull = kARawFree + kStages, kAccEmpty = kAccFull + 2, kSmpFull = kAccEmpty + 2,
               kSmpEmpty = kSmpFull + 2, kNumBars = kSmpEmpty + 2;
 static_assert(kNumBars <= 32, "barrier block is 32 words");
 
-constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)kStages * STAGE_BYTES + 2 * 128 * sizeof(int64_t) +
-                              2 * 128 * sizeof(double) + 32 * sizeof(uint64_t) + 64 + 40 * sizeof(double);
+constexpr int A_OFF = kStages * STAGE_BYTES;  // raw A stages follow the B stages
+constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)kStages * (STAGE_BYTES + SUB_BYTES) +
+                              5 * 128 * sizeof(int64_t) + 2 * 128 * sizeof(double) + 32 * sizeof(uint64_t) + 64 +
+                              72 * sizeof(double);
 
 enum : int32_t { kKFast = 0, kMNFast = 1, kAnyLayout = 2 };  // B staging layouts
-enum : int32_t { kAVec = 0, kAScalar = 1 };                   // A load modes
-enum : int32_t { kFlagCVec = 1, kFlagTmaB = 2 };              // launch flags
+enum : int32_t { kFlagCVec = 1, kFlagTmaB = 2, kFlagTmaA = 32, // launch flags
+                 kFlagDbgNoSample = 4, kFlagDbgNoLo = 8,       // timing experiments only (CTN_T32_DEBUG): wrong results
+                 kFlagTrace = 16 };                            // CTA 0 records a time line of its pipeline events
+
+// time line of CTA 0 (CTN_T32_DEBUG=16): SM clock of event `ev` at k-block / tile ordinal `it`, one
+// fire-and-forget store per event into a fixed slot (no atomics: the probe must not stall the warp)
+constexpr int kTraceEvents = 32, kTraceIts = 1024;
+__device__ long long g_trace[kTraceEvents * kTraceIts];
+__device__ __forceinline__ void trace(int flags, int ev, unsigned it) {
+  if ((flags & kFlagTrace) && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it < (unsigned)kTraceIts)
+    g_trace[ev * kTraceIts + it] = clock64();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -155,6 +171,15 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                : "memory");
 }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// stores through the global window (the output pointer comes out of a table, so the compiler would
+// otherwise emit generic stores)
+__device__ __forceinline__ void st_global(float* p, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_global4(float* p, float x, float y, float z, float w) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "f"(x), "f"(y), "f"(z), "f"(w)
+               : "memory");
+}
 __device__ __forceinline__ void bar_named(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kRoleThreads) : "memory"); }
 
 // TMA: one tensor box, global -> shared, completion counted in bytes on an mbarrier
@@ -182,6 +207,10 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gmem, boo
 __device__ __forceinline__ void cp_async4(uint32_t saddr, const void* gmem, bool valid) {
   const int sz = valid ? 4 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(gmem), "r"(sz) : "memory");
+}
+// the mbarrier receives one arrival once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -224,73 +253,8 @@ __device__ __forceinline__ int b_elem_offset(int n, int k) {
   return (n >> 3) * 1024 + (n & 7) * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
 }
 
-// summed-mode strides of one operand, held in registers (n <= 4)
-struct KInfo {
-  int n;
-  int64_t e[4], s[4];
-  __device__ __forceinline__ int64_t off(int64_t k) const {
-    if (n == 1) return k * s[0];
-    int64_t o = 0;
-#pragma unroll
-    for (int i = 3; i >= 0; --i) {
-      if (i < n) {
-        const int64_t q = k / e[i], r = k - q * e[i];
-        k = q;
-        o += r * s[i];
-      }
-    }
-    return o;
-  }
-};
-__device__ __forceinline__ KInfo load_kinfo(const GemmDev& g, bool use_b) {
-  KInfo k;
-  k.n = g.n_k;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    k.e[i] = i < g.n_k ? g.k[i].extent : 1;
-    k.s[i] = i < g.n_k ? (use_b ? g.k[i].sb : g.k[i].sa) : 0;
-  }
-  return k;
-}
-
 template <int LAYOUT>
 struct ChunkCount { static constexpr int N = (LAYOUT == kAnyLayout) ? 32 : 8; };
-
-template <int LAYOUT>
-__device__ __forceinline__ void chunk_sources(const float* (&src)[ChunkCount<LAYOUT>::N], const float* base,
-                                              const int64_t* row_off, int t) {
-#pragma unroll
-  for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i) {
-    int row, kk;
-    chunk_offset<LAYOUT>(i, t, row, kk);
-    const int64_t ro = row_off[row];
-    src[i] = ro >= 0 ? base + ro : nullptr;
-  }
-}
-
-template <int LAYOUT>
-__device__ __forceinline__ void issue_copy(uint32_t raw_tile, const float* const (&src)[ChunkCount<LAYOUT>::N],
-                                           const int (&soff)[ChunkCount<LAYOUT>::N], const int (&kk)[ChunkCount<LAYOUT>::N],
-                                           const KInfo& ki, int64_t k0, int64_t K, bool interior) {
-  if (interior && ki.n == 1) {
-    const int64_t sk = ki.s[0];
-#pragma unroll
-    for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i) {
-      const float* p = src[i] + (k0 + kk[i]) * sk;
-      if (LAYOUT == kAnyLayout) cp_async4(raw_tile + soff[i], p, true);
-      else cp_async16(raw_tile + soff[i], p, true);
-    }
-    return;
-  }
-#pragma unroll
-  for (int i = 0; i < ChunkCount<LAYOUT>::N; ++i) {
-    const int64_t k = k0 + kk[i];
-    const bool valid = src[i] != nullptr && k < K;
-    const float* p = valid ? src[i] + ki.off(k) : src[0];
-    if (LAYOUT == kAnyLayout) cp_async4(raw_tile + soff[i], p, valid);
-    else cp_async16(raw_tile + soff[i], p, valid);
-  }
-}
 
 __device__ __forceinline__ float residual_tf32(float x) {
   // the tensor core uses trunc(x) as `hi` (it truncates fp32 operands to tf32); the residual is exact
@@ -348,6 +312,8 @@ __device__ __forceinline__ TileCoord decode_tile(uint32_t w, uint32_t tilesM, ui
 }
 
 __device__ __forceinline__ int64_t mode_offset(const GemmMode* modes, int n, int64_t idx, int which /*0 sa 1 sb 2 sc 3 sw*/) {
+  if (n == 1)  // one fused mode (the common case): no division
+    return idx * (which == 0 ? modes[0].sa : which == 1 ? modes[0].sb : which == 2 ? modes[0].sc : modes[0].sw);
   int64_t o = 0;
   for (int i = n - 1; i >= 0; --i) {
     const int64_t e = modes[i].extent;
@@ -358,29 +324,54 @@ __device__ __forceinline__ int64_t mode_offset(const GemmMode* modes, int n, int
   return o;
 }
 
+// Four block-wide sums in one pass, fixed order (deterministic).  Results valid in all threads.
+__device__ __forceinline__ void block_sum4(double (&v)[4], double* sm /* >= 4 * 17 doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sm[i * 17 + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp < 4) {
+    double t = lane < nw ? sm[warp * 17 + lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) sm[warp * 17 + 16] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = sm[i * 17 + 16];
+}
+
 // several summed modes in A: per-element decomposition, deliberately NOT inlined (it is called from a
 // fully unrolled 32-element loop in 24 kernel instantiations)
 __device__ __noinline__ int64_t k_offset_a(const GemmDev& g, int64_t k) { return mode_offset(g.k, g.n_k, k, 0); }
+__device__ __noinline__ int64_t k_offset_b(const GemmDev& g, int64_t k) { return mode_offset(g.k, g.n_k, k, 1); }
 
-template <int LB, int AMODE, bool FUSED, bool TMAB>
+template <int LA, int LB, bool FUSED, bool TMAB, bool TMAA>
 __global__ void __launch_bounds__(kThreadsT, 1)
-    gemm_tf32x3_kernel(const StepDev* __restrict__ steps, const GemmDev* __restrict__ gemms, int step_idx, DevState d,
-                       int launch_flags, const __grid_constant__ CUtensorMap tmap_b) {
+    gemm_tf32x3_kernel(const __grid_constant__ StepDev s, const __grid_constant__ GemmDev g, DevState d,
+                       int launch_flags, const __grid_constant__ CUtensorMap tmap_b,
+                       const __grid_constant__ CUtensorMap tmap_a) {
+  // (the step and its GEMM view travel in the kernel parameters: no dependent descriptor loads from
+  // global memory at the head of every launch)
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   unsigned char* smem = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
-  unsigned char* tiles = smem;
-  int64_t* colB = reinterpret_cast<int64_t*>(smem + kStages * STAGE_BYTES);  // B producers: column -> offset in B
-  int64_t* colC = colB + 128;                                                 // epilogue: column -> offset in C
-  double* sample = reinterpret_cast<double*>(colC + 128);                     // [2][128] exact entries
+  unsigned char* tiles = smem;           // B stages: [hi | lo] x kStages
+  unsigned char* atiles = smem + A_OFF;  // raw A stages
+  int64_t* coltab = reinterpret_cast<int64_t*>(smem + kStages * (STAGE_BYTES + SUB_BYTES));  // [2][128] B producers
+  int64_t* rowtab = coltab + 256;                                                             // [2][128] A producers
+  int64_t* colC = rowtab + 256;                                                               // [128]    epilogue
+  double* sample = reinterpret_cast<double*>(colC + 128);                                     // [2][128] exact entries
   uint64_t* bars = reinterpret_cast<uint64_t*>(sample + 2 * 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 4);
   double* red = reinterpret_cast<double*>(tmem_slot + 16);
   __shared__ bool last_block;
 
-  const StepDev& s = steps[step_idx];
-  const GemmDev& g = gemms[s.gemm_off];
   const float* A = (const float*)d.ptrs[s.in_slot[0]];
   const float* Bp = (const float*)d.ptrs[s.in_slot[1]];
   float* C = (float*)d.ptrs[s.out_slot];
@@ -391,6 +382,9 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   const uint32_t tilesM = (uint32_t)((M + BM - 1) / BM), tilesN = (uint32_t)((N + npt - 1) / npt);
   const uint32_t total = (uint32_t)g.B * tilesM * tilesN;
   const int nk = (int)((K + BKF - 1) / BKF);
+  // this CTA's share of the work as one flat sequence of k-blocks: producers prefetch across tiles
+  const uint32_t my_tiles = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+  const uint32_t total_it = my_tiles * (uint32_t)nk;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -400,16 +394,18 @@ __global__ void __launch_bounds__(kThreadsT, 1)
 
   if (tid == 0) {
     for (int st = 0; st < kStages; ++st) {
-      mbar_init(bar(kFullA + st), 4);   // one elected lane per A-producer warp
-      mbar_init(bar(kFullB + st), 4);   // one elected lane per B-producer warp
-      mbar_init(bar(kEmpty + st), 5);   // tcgen05.commit + the four sampling warps
-      mbar_init(bar(kTmaFull + st), 1); // TMA: one arrive.expect_tx + the transaction bytes
+      mbar_init(bar(kFullA + st), 4);    // one elected lane per A-producer warp
+      mbar_init(bar(kFullB + st), 4);    // one elected lane per B-producer warp
+      mbar_init(bar(kEmpty + st), 4);    // tcgen05.commit + the three sampling warps
+      mbar_init(bar(kTmaFull + st), 1);  // TMA: one arrive.expect_tx + the transaction bytes
+      mbar_init(bar(kARaw + st), TMAA ? 1 : kRoleThreads);  // TMA transaction / cp.async completion of every loader thread
+      mbar_init(bar(kARawFree + st), 7);         // one elected lane per A-converter warp and per sampler warp
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kAccFull + b), 1);
       mbar_init(bar(kAccEmpty + b), 4);
-      mbar_init(bar(kSmpFull + b), 4);
-      mbar_init(bar(kSmpEmpty + b), 4);
+      mbar_init(bar(kSmpFull + b), 3);
+      mbar_init(bar(kSmpEmpty + b), 3);
     }
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -424,54 +420,44 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 12) trace(launch_flags, 0, 0);
 
   double local_abs = 0.0, local_abs_t = 0.0;  // sum|out| and (fused) sum|X|         (epilogue threads)
   double s_exact = 0.0, s_tc = 0.0;           // sampled entries: exact vs tensor core (epilogue threads)
 
   if (warp < 4) {
-    // =========================== A producers ===========================
+    // =========================== A converters ===========================
+    // raw A tile (staged by the loader warps) -> registers -> TMEM (hi, lo)
     const int r = tid;
-    // summed-mode strides of A: one mode is the common case (kept in a register); more are
-    // decomposed per element from the descriptor (slow path, but any view works)
-    const int n_k = g.n_k;
-    const int64_t sk0 = g.k[0].sa;
-    uint32_t it = 0, tile_iter = 0;
-    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
-      const TileCoord tc = decode_tile(w, tilesM, tilesN);
-      const int64_t m = (int64_t)tc.tm * BM + r;
-      const bool row_ok = m < M;
-      int64_t oa = 0;
-      if (row_ok) oa = mode_offset(g.m, g.n_m, m, 0);
-      if (g.n_batch > 0) oa += mode_offset(g.batch, g.n_batch, tc.b, 0);
-      const float* arow = A + oa;
-      const uint32_t buf = tile_iter & 1u;
-      const int scol = (int)(((tile_iter + (uint32_t)warp) & 3u) * 32u + (((uint32_t)lane * 7u + tile_iter * 3u) & 31u));
-      double sacc = 0.0;
-
-      auto load_a = [&](float (&v)[32], int kb) {
-        const int64_t k0 = (int64_t)kb * BKF;
-        if (AMODE == kAVec && row_ok && k0 + BKF <= K) {
-          const float4* p = reinterpret_cast<const float4*>(arow + k0);
+    uint32_t it = 0;
+    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
+        MBAR_WAIT(kARaw + st, ph);  // every loader thread's copies of this k-block have landed
+        if (warp == 0) trace(launch_flags, 1, it);
+        float v[32];
+        {
+          const unsigned char* at = atiles + st * SUB_BYTES;
+          if (LA == kMNFast && TMAA) {  // one TMA box (128 rows, 32 k), no swizzle: [k][row]
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 x = __ldg(p + c);
-            v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
-          }
-        } else if (row_ok && k0 + BKF <= K && n_k == 1) {
-          const float* p = arow + k0 * sk0;
+            for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + j * 512 + r * 4);
+          } else if (LA == kMNFast) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __ldg(p + j * sk0);
-        } else {
-#pragma unroll  // (full unroll: a dynamic index would push v[] into local memory for every path)
-          for (int j = 0; j < 32; ++j) {
-            const int64_t k = k0 + j;
-            v[j] = (row_ok && k < K) ? __ldg(arow + (n_k == 1 ? k * sk0 : k_offset_a(g, k))) : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + b_elem_offset<kMNFast, false>(r, j));
+          } else {
+            const int base = (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              // chunk c of row r sits at position c ^ (r & 7): eight consecutive rows hit eight bank groups
+              const float4 x = *reinterpret_cast<const float4*>(at + base + ((c ^ (r & 7)) << 4));
+              v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+            }
           }
         }
-      };
-      auto a_step = [&](const float (&v)[32]) {
-        const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
-        MBAR_WAIT(kEmpty + st, ph ^ 1u);  // the MMAs that read this TMEM stage have completed
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kARawFree + st));  // this warp has read the stage: it may be refilled
+        MBAR_WAIT(kEmpty + st, ph ^ 1u);                   // the MMAs that read this TMEM stage have completed
+        if (warp == 0) trace(launch_flags, 2, it);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + kAStageCol0 + st * 64u;
         {
@@ -491,46 +477,8 @@ __global__ void __launch_bounds__(kThreadsT, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kFullA + st));
-        // ---- sampled exact entry (float64) of this row: column scol of the raw B tile ----
-        MBAR_WAIT(kFullB + st, ph);
-        const unsigned char* bt = tiles + st * STAGE_BYTES;
-        if (LB == kMNFast) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float b = *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j));
-            sacc = fma((double)v[j], (double)b, sacc);
-          }
-        } else {
-          const int base = (scol >> 3) * 1024 + (scol & 7) * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 b = *reinterpret_cast<const float4*>(bt + base + ((c ^ (scol & 7)) << 4));
-            sacc = fma((double)v[4 * c], (double)b.x, sacc);
-            sacc = fma((double)v[4 * c + 1], (double)b.y, sacc);
-            sacc = fma((double)v[4 * c + 2], (double)b.z, sacc);
-            sacc = fma((double)v[4 * c + 3], (double)b.w, sacc);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kEmpty + st));
-        ++it;
-      };
-
-      float v0[32], v1[32];
-      load_a(v0, 0);
-      if (nk > 1) load_a(v1, 1);
-      for (int kb = 0; kb < nk; kb += 2) {
-        a_step(v0);
-        if (kb + 2 < nk) load_a(v0, kb + 2);
-        if (kb + 1 < nk) {
-          a_step(v1);
-          if (kb + 3 < nk) load_a(v1, kb + 3);
-        }
+        if (warp == 0) trace(launch_flags, 3, it);
       }
-      MBAR_WAIT(kSmpEmpty + buf, ((tile_iter >> 1) & 1u) ^ 1u);
-      sample[buf * 128 + r] = sacc;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kSmpFull + buf));
     }
   } else if (warp < 8) {
     // =========================== epilogue ===========================
@@ -550,29 +498,44 @@ __global__ void __launch_bounds__(kThreadsT, 1)
         if (FUSED) ow = mode_offset(g.m, g.n_m, m, 3);
       }
       if (g.n_batch > 0) oc += mode_offset(g.batch, g.n_batch, tc.b, 2);
-      bar_named(2);  // every epilogue thread is done with the previous tile's column table
-      {
-        int64_t off = -1;
+      // column offsets: one column mode (the common case) is plain arithmetic; several modes go through a table
+      const bool lin = g.n_n == 1;
+      const int64_t scn = g.n[0].sc;
+      const int ncols = (int)min((int64_t)npt, N - (int64_t)tc.tn * npt);  // valid columns of this tile
+      if (!lin) {
+        bar_named(2);  // every epilogue thread is done with the previous tile's column table
+        int64_t off = 0;
         if (te < npt) {
           const int64_t n = (int64_t)tc.tn * npt + te;
           if (n < N) off = mode_offset(g.n, g.n_n, n, 2);
         }
         colC[te] = off;
+        bar_named(2);
       }
-      bar_named(2);
+      if (q == 0) trace(launch_flags, 17, tile_iter);
+      float wv4[4] = {0.f, 0.f, 0.f, 0.f};  // fused consumer: this row's weights (pr <= 4), off the critical path
+      if (FUSED && row_ok) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+          if (rr < pr) wv4[rr] = __ldg(Wp + ow + (int64_t)rr * g.fuse_sw) * alpha_w;
+      }
       const uint32_t buf = tile_iter & 1u;
       MBAR_WAIT(kAccFull + buf, (tile_iter >> 1) & 1u);
+      if (q == 0) trace(launch_flags, 10, tile_iter);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol0 + buf * 128u;
       const int schunk = (int)((tile_iter + (uint32_t)q) & 3u), sidx = (int)(((uint32_t)lane * 7u + tile_iter * 3u) & 31u);
       float tcval = 0.f, lf = 0.f, lt = 0.f;
-      float* Crow = C + oc;
+      float* Crow = C + oc + (lin ? (int64_t)tc.tn * npt * scn : 0);
+      // (rows / columns outside the problem were zero-filled on the way in, so their accumulator entries are
+      // exact zeros: the sums below need no predicate, only the stores do)
       if (!FUSED) {
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t a[32];
           tc_ld32(tbase + (uint32_t)cc * 32u, a);
           tc_ld_wait();
+          if (q == 0) trace(launch_flags, 13 + cc, tile_iter);
           if (cc == 3) {
             // accumulator fully read: the MMA warp may start the tile after next in this buffer
             tc_fence_before();
@@ -587,26 +550,21 @@ __global__ void __launch_bounds__(kThreadsT, 1)
             if (c_vec) {
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const int64_t co = colC[cc * 32 + 4 * j4];
-                if (co >= 0) {
-                  float4 v;
-                  v.x = __uint_as_float(a[4 * j4]) * alpha;
-                  v.y = __uint_as_float(a[4 * j4 + 1]) * alpha;
-                  v.z = __uint_as_float(a[4 * j4 + 2]) * alpha;
-                  v.w = __uint_as_float(a[4 * j4 + 3]) * alpha;
-                  *reinterpret_cast<float4*>(Crow + co) = v;
-                  lf += (fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w));
-                }
+                const int c0 = cc * 32 + 4 * j4;
+                float* p = lin ? Crow + c0 : Crow + colC[c0];  // (c_vec: unit column stride)
+                const float x = __uint_as_float(a[4 * j4]) * alpha, y = __uint_as_float(a[4 * j4 + 1]) * alpha;
+                const float z = __uint_as_float(a[4 * j4 + 2]) * alpha, w4 = __uint_as_float(a[4 * j4 + 3]) * alpha;
+                if (c0 < ncols) st_global4(p, x, y, z, w4);
+                lf += (fabsf(x) + fabsf(y)) + (fabsf(z) + fabsf(w4));
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const int64_t co = colC[cc * 32 + j];
+                const int c0 = cc * 32 + j;
+                float* p = lin ? Crow + (int64_t)c0 * scn : Crow + colC[c0];
                 const float v = __uint_as_float(a[j]) * alpha;
-                if (co >= 0) {
-                  Crow[co] = v;
-                  lf += fabsf(v);
-                }
+                if (c0 < ncols) st_global(p, v);
+                lf += fabsf(v);
               }
             }
           }
@@ -635,7 +593,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
               for (int j = 0; j < 32; ++j) tcval = (j == sidx) ? __uint_as_float(a[j]) : tcval;
             }
             // rows / columns outside the problem were zero-filled, so their entries are exact zeros
-            const float wv = row_ok ? __ldg(Wp + ow + (int64_t)rr * g.fuse_sw) * alpha_w : 0.f;
+            const float wv = rr == 0 ? wv4[0] : rr == 1 ? wv4[1] : rr == 2 ? wv4[2] : wv4[3];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float t = __uint_as_float(a[j]) * alpha;  // the un-materialised X entry
@@ -646,148 +604,331 @@ __global__ void __launch_bounds__(kThreadsT, 1)
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int64_t co = colC[nc * 32 + j];
-              if (co >= 0) {
-                Crow[co] = o[j];
-                lf += fabsf(o[j]);
-              }
+              const int c0 = nc * 32 + j;
+              float* p = lin ? Crow + (int64_t)c0 * scn : Crow + colC[c0];
+              if (c0 < ncols) st_global(p, o[j]);
+              lf += fabsf(o[j]);
             }
           }
         }
       }
       local_abs += (double)lf;
       local_abs_t += (double)lt;
-      MBAR_WAIT(kSmpFull + buf, (tile_iter >> 1) & 1u);
-      const double ex = sample[buf * 128 + r];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kSmpEmpty + buf));
-      s_exact += fabs(ex);
-      s_tc += fabs((double)tcval);
+      if (q == 0) trace(launch_flags, 12, tile_iter);
+      if ((((uint32_t)q - tile_iter) & 3u) != 3u) {  // this quarter's rows are sampled in this tile (see the samplers)
+        MBAR_WAIT(kSmpFull + buf, (tile_iter >> 1) & 1u);
+        const double ex = sample[buf * 128 + r];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kSmpEmpty + buf));
+        s_exact += fabs(ex);
+        s_tc += fabs((double)tcval);
+      }
     }
   } else if (warp < 12) {
-    // =========================== B producers ===========================
+    // =========================== loaders (A and B) + B converters ===========================
     const int tb = tid - 2 * kRoleThreads;
-    const KInfo kib = load_kinfo(g, true);
-    int soffB[ChunkCount<LB>::N], kkB[ChunkCount<LB>::N];
-#pragma unroll
-    for (int i = 0; i < ChunkCount<LB>::N; ++i) {
-      int row;
-      soffB[i] = chunk_offset<LB>(i, tb, row, kkB[i]);
-    }
-    uint32_t it_base = 0;
-    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, it_base += (uint32_t)nk) {
-      const TileCoord tc = decode_tile(w, tilesM, tilesN);
-      if (TMAB) {
-        // ---- TMA: an elected thread issues ONE tensor box per k-block; all 128 threads form the lo tile ----
-        auto issue = [&](int kb) {
-          if (tb != 0) return;
-          const uint32_t it = it_base + (uint32_t)kb, st = it & (kStages - 1), ph = (it / kStages) & 1u;
-          MBAR_WAIT(kEmpty + st, ph ^ 1u);
-          mbar_expect_tx(bar(kTmaFull + st), (uint32_t)SUB_BYTES);
-          const uint32_t dst = smem_u32(tiles + st * STAGE_BYTES);
-          if (LB == kMNFast) {
-            // dims: (32 n-inner, k, n-outer [32-column blocks], r or batch)
-            tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), 0, kb * BKF, tc.tn * (npt >> 5), FUSED ? 0 : tc.b);
-          } else {
-            // dims: (k, n, batch, 1)
-            tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), kb * BKF, tc.tn * BN, tc.b, 0);
-          }
-        };
-        for (int j = 0; j < kStages - 1 && j < nk; ++j) issue(j);  // three boxes in flight
-        for (int kb = 0; kb < nk; ++kb) {
-          const uint32_t it = it_base + (uint32_t)kb, st = it & (kStages - 1), ph = (it / kStages) & 1u;
-          MBAR_WAIT(kTmaFull + st, ph);
-          unsigned char* stage = tiles + st * STAGE_BYTES;
-          make_lo_linear(stage, stage + SUB_BYTES, tb);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(kFullB + st));
-          if (kb + kStages - 1 < nk) issue(kb + kStages - 1);
-        }
-        continue;
+    const int n_k = g.n_k;
+    const int64_t ska = g.k[0].sa, skb = g.k[0].sb;
+    constexpr int NA = ChunkCount<LA>::N, NB = ChunkCount<LB>::N;
+    constexpr bool kPtrA = LA != kAnyLayout && !TMAA, kPtrB = LB != kAnyLayout && !TMAB;  // chunk pointers kept in registers
+    // issue cursor (runs kStages - 1 k-blocks ahead of the conversion loop, across tiles)
+    uint32_t it_i = 0, wi = blockIdx.x, ji = 0;
+    int kbi = 0;
+    TileCoord tci = decode_tile(total > 0 ? min(wi, total - 1) : 0, tilesM, tilesN);
+    const float* abase_i = A;
+    const float* bbase_i = Bp;
+    bool rows_full_i = false, cols_full_i = false;
+    const float* srcA[kPtrA ? NA : 1];
+    const float* srcB[kPtrB ? NB : 1];
+    auto setup_issue_tile = [&]() {
+      tci = decode_tile(wi, tilesM, tilesN);
+      int64_t* rt = rowtab + (ji & 1u) * 128;
+      int64_t* ct = coltab + (ji & 1u) * 128;
+      if (!TMAA) {
+        const int64_t m = (int64_t)tci.tm * BM + tb;
+        rt[tb] = m < M ? mode_offset(g.m, g.n_m, m, 0) : -1;
       }
-      int64_t offBb = 0;
-      if (g.n_batch > 0) offBb = mode_offset(g.batch, g.n_batch, tc.b, 1);
-      bar_named(1);  // every B producer is done with the previous tile's column table
-      {
+      if (!TMAB) {
         const int rr = FUSED ? tb / npt : 0;
-        const int64_t n = FUSED ? (int64_t)tc.tn * npt + (tb - rr * npt) : (int64_t)tc.tn * BN + tb;
+        const int64_t n = FUSED ? (int64_t)tci.tn * npt + (tb - rr * npt) : (int64_t)tci.tn * BN + tb;
         int64_t ob = -1;
         if (n < N) {
           ob = mode_offset(g.n, g.n_n, n, 1);
           if (FUSED) ob += (int64_t)rr * g.fuse_sb;
         }
-        colB[tb] = ob;
+        ct[tb] = ob;
       }
-      bar_named(1);
-      const float* srcB[ChunkCount<LB>::N];
-      chunk_sources<LB>(srcB, Bp + offBb, colB, tb);
-      const bool cols_full = ((int64_t)tc.tn + 1) * npt <= N;
-      auto prefetch = [&](int kb) {
-        const uint32_t it = it_base + (uint32_t)kb, st = it & (kStages - 1), ph = (it / kStages) & 1u;
-        MBAR_WAIT(kEmpty + st, ph ^ 1u);  // tensor core and samplers have finished with this stage
-        const uint32_t stage = smem_u32(tiles + st * STAGE_BYTES);
-        const bool interior = cols_full && (int64_t)(kb + 1) * BKF <= K;
-        issue_copy<LB>(stage, srcB, soffB, kkB, kib, (int64_t)kb * BKF, K, interior);
-      };
+      abase_i = A + (g.n_batch > 0 ? mode_offset(g.batch, g.n_batch, tci.b, 0) : 0);
+      bbase_i = Bp + (g.n_batch > 0 ? mode_offset(g.batch, g.n_batch, tci.b, 1) : 0);
+      rows_full_i = ((int64_t)tci.tm + 1) * BM <= M;
+      cols_full_i = ((int64_t)tci.tn + 1) * npt <= N;
+      if (!(TMAA && TMAB)) bar_named(1);  // tables complete (their other halves may still be in use for the previous tile)
+      if (kPtrA) {
 #pragma unroll
-      for (int j = 0; j < kStages - 1; ++j) {
-        if (j < nk) prefetch(j);
-        cp_async_commit();
+        for (int i = 0; i < NA; ++i) {
+          int row, kk;
+          chunk_offset<LA>(i, tb, row, kk);
+          const int64_t ro = rt[row];
+          srcA[kPtrA ? i : 0] = ro >= 0 ? abase_i + ro + (n_k == 1 ? (int64_t)kk * ska : 0) : nullptr;
+        }
       }
-      for (int kb = 0; kb < nk; ++kb) {
-        cp_async_wait<kStages - 2>();  // this thread's chunks of k-block kb have landed
-        const uint32_t it = it_base + (uint32_t)kb, st = it & (kStages - 1);
-        unsigned char* stage = tiles + st * STAGE_BYTES;
-        make_lo<LB>(stage, stage + SUB_BYTES, soffB);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kFullB + st));
-        if (kb + kStages - 1 < nk) prefetch(kb + kStages - 1);
-        cp_async_commit();
+      if (kPtrB) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          int row, kk;
+          chunk_offset<LB>(i, tb, row, kk);
+          const int64_t ro = ct[row];
+          srcB[kPtrB ? i : 0] = ro >= 0 ? bbase_i + ro + (n_k == 1 ? (int64_t)kk * skb : 0) : nullptr;
+        }
       }
-      cp_async_wait<0>();
+    };
+    auto issue_next = [&]() {
+      if (it_i >= total_it) return;
+      const uint32_t st = it_i & (kStages - 1), ph = (it_i / kStages) & 1u;
+      const int64_t k0 = (int64_t)kbi * BKF;
+      const bool k_in = k0 + BKF <= K && n_k == 1;
+      // ---- A: raw tile, 16-byte cp.async; completion is counted on the stage's mbarrier ----
+      if (TMAA) {
+        // ---- A: ONE TMA tensor box per k-block (K-fast: (32 k, 128 rows) SWIZZLE_128B; M-fast: (128 rows, 32 k)) ----
+        if (tb == 0) {
+          MBAR_WAIT(kARawFree + st, ph ^ 1u);  // the four converter warps have read the previous contents
+          mbar_expect_tx(bar(kARaw + st), (uint32_t)SUB_BYTES);
+          const uint32_t dst = smem_u32(atiles + st * SUB_BYTES);
+          if (LA == kMNFast) tma_load_4d(dst, &tmap_a, bar(kARaw + st), tci.tm * BM, kbi * BKF, tci.b, 0);
+          else tma_load_4d(dst, &tmap_a, bar(kARaw + st), kbi * BKF, tci.tm * BM, tci.b, 0);
+        }
+      } else {
+      MBAR_WAIT(kARawFree + st, ph ^ 1u);  // the four converter warps have read the previous contents
+      if (warp == 8) trace(launch_flags, 21, it_i);
+      {
+        const uint32_t stage = smem_u32(atiles + st * SUB_BYTES);
+        const int64_t* rt = rowtab + (ji & 1u) * 128;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+          int row, kk;
+          const int soff = chunk_offset<LA>(i, tb, row, kk);
+          if (kPtrA && n_k == 1) {
+            const float* base = srcA[kPtrA ? i : 0];
+            const bool valid = base != nullptr && (k_in || k0 + kk < K);
+            cp_async16(stage + soff, valid ? base + k0 * ska : A, valid);
+          } else {
+            const int64_t ro = rt[row];
+            const int64_t k = k0 + kk;
+            const bool valid = ro >= 0 && k < K;
+            const float* src = valid ? abase_i + ro + (n_k == 1 ? k * ska : k_offset_a(g, k)) : A;
+            if (LA == kAnyLayout) cp_async4(stage + soff, src, valid);
+            else cp_async16(stage + soff, src, valid);
+          }
+        }
+        if (warp == 8) trace(launch_flags, 22, it_i);
+        cp_async_mbar_arrive(bar(kARaw + st));
+      }
+      }
+      if (warp == 8) trace(launch_flags, 23, it_i);
+      // ---- B: one TMA tensor box issued by an elected thread, or cp.async chunks ----
+      if (TMAB) {
+        if (tb == 0) {
+          MBAR_WAIT(kEmpty + st, ph ^ 1u);  // tensor core and samplers have finished with this stage
+          trace(launch_flags, 24, it_i);
+          mbar_expect_tx(bar(kTmaFull + st), (uint32_t)SUB_BYTES);
+          const uint32_t dst = smem_u32(tiles + st * STAGE_BYTES);
+          if (LB == kMNFast)  // dims: (32 n-inner, k, n-outer [32-column blocks], r or batch)
+            tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), 0, kbi * BKF, tci.tn * (npt >> 5), FUSED ? 0 : tci.b);
+          else                // dims: (k, n, batch, 1)
+            tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), kbi * BKF, tci.tn * BN, tci.b, 0);
+        }
+      } else {
+        MBAR_WAIT(kEmpty + st, ph ^ 1u);
+        const uint32_t stage = smem_u32(tiles + st * STAGE_BYTES);
+        const int64_t* ct = coltab + (ji & 1u) * 128;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          int row, kk;
+          const int soff = chunk_offset<LB>(i, tb, row, kk);
+          if (kPtrB && n_k == 1) {
+            const float* base = srcB[kPtrB ? i : 0];
+            const bool valid = base != nullptr && (k_in || k0 + kk < K);
+            cp_async16(stage + soff, valid ? base + k0 * skb : Bp, valid);
+          } else {
+            const int64_t ro = ct[row];
+            const int64_t k = k0 + kk;
+            const bool valid = ro >= 0 && k < K;
+            const float* src = valid ? bbase_i + ro + (n_k == 1 ? k * skb : k_offset_b(g, k)) : Bp;
+            if (LB == kAnyLayout) cp_async4(stage + soff, src, valid);
+            else cp_async16(stage + soff, src, valid);
+          }
+        }
+      }
+      if (warp == 8) trace(launch_flags, 4, it_i);
+      ++it_i;
+      if (++kbi == nk) {
+        kbi = 0;
+        wi += gridDim.x;
+        ++ji;
+        if (it_i < total_it) setup_issue_tile();
+      }
+    };
+    if (total_it > 0) setup_issue_tile();
+    if (warp == 8) trace(launch_flags, 20, 0);
+#pragma unroll 1
+    for (int n = 0; n < kStages - 1; ++n) {
+      issue_next();
+      cp_async_commit();
     }
-  } else {
+    int soffB[NB];
+    if (!TMAB) {
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        int row, kk;
+        soffB[i] = chunk_offset<LB>(i, tb, row, kk);
+      }
+    }
+    for (uint32_t it = 0; it < total_it; ++it) {
+      const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
+      unsigned char* stage = tiles + st * STAGE_BYTES;
+      if (TMAB) {
+        MBAR_WAIT(kTmaFull + st, ph);
+        if (warp == 8) trace(launch_flags, 5, it);
+        if (!(launch_flags & kFlagDbgNoLo)) make_lo_linear(stage, stage + SUB_BYTES, tb);
+      } else {
+        cp_async_wait<kStages - 2>();  // this thread's chunks of k-block `it` have landed
+        if (warp == 8) trace(launch_flags, 5, it);
+        if (!(launch_flags & kFlagDbgNoLo)) make_lo<LB>(stage, stage + SUB_BYTES, soffB);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kFullB + st));
+      if (warp == 8) trace(launch_flags, 6, it);
+      issue_next();
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+  } else if (warp == 12) {
     // =========================== MMA issuer (warp 12) ===========================
     // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, tf32 x tf32, A (TMEM) K-major
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((LB == kMNFast ? 1u : 0u) << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    uint32_t it = 0, tile_iter = 0;
-    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
-      const uint32_t buf = tile_iter & 1u;
-      MBAR_WAIT(kAccEmpty + buf, ((tile_iter >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + kAccCol0 + buf * 128u;
-      for (int kb = 0; kb < nk; ++kb, ++it) {
-        const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
-        MBAR_WAIT(kFullA + st, ph);
-        MBAR_WAIT(kFullB + st, ph);
+    // B descriptors: K-major SWIZZLE_128B; MN-major SWIZZLE_128B_BASE32B with the atom strides of whoever
+    // filled the tile (cp.async: MN-atoms 512 B / K-atoms 2048 B; TMA box: 4096 B / 512 B)
+    const uint32_t b_lbo = (LB == kMNFast) ? (TMAB ? 4096u : 512u) : 16u;
+    const uint32_t b_sbo = (LB == kMNFast) ? (TMAB ? 512u : 2048u) : 1024u;
+    const uint32_t b_ty = (LB == kMNFast) ? 1u : 2u;
+    if (lane == 0) {  // a single thread issues everything: no warp-level synchronisation in the loop
+      uint32_t it = 0, tile_iter = 0;
+      bool ready = false;  // operands of k-block `it` already awaited (done while the previous MMAs ran)
+      for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1u;
+        MBAR_WAIT(kAccEmpty + buf, ((tile_iter >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer
         tc_fence_after();
-        if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + kAccCol0 + buf * 128u;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
+          if (!ready) {
+            MBAR_WAIT(kFullA + st, ph);
+            trace(launch_flags, 7, it);
+            MBAR_WAIT(kFullB + st, ph);
+            trace(launch_flags, 8, it);
+          }
+          ready = false;
+          tc_fence_after();
           const uint32_t a_col = tmem_base + kAStageCol0 + st * 64u;
           const uint32_t sb = smem_u32(tiles + st * STAGE_BYTES);
           const uint32_t b_hi = sb, b_lo = sb + SUB_BYTES;
-          // B descriptors: K-major SWIZZLE_128B; MN-major SWIZZLE_128B_BASE32B with the atom strides of
-          // whoever filled the tile (cp.async: MN-atoms 512 B / K-atoms 2048 B; TMA box: 4096 B / 512 B)
-          const uint32_t b_lbo = (LB == kMNFast) ? (TMAB ? 4096u : 512u) : 16u;
-          const uint32_t b_sbo = (LB == kMNFast) ? (TMAB ? 512u : 2048u) : 1024u;
-          const uint32_t b_ty = (LB == kMNFast) ? 1u : 2u;
 #pragma unroll
           for (int ks = 0; ks < BKF / 8; ++ks) {
             // one UMMA_K = 8 floats: 32 bytes along K (K-major) or two k-atoms (MN-major)
             const uint32_t bo = (LB == kMNFast) ? (uint32_t)ks * 2u * b_sbo : (uint32_t)ks * 32u;
             const uint64_t dbh = make_desc(b_hi + bo, b_lbo, b_sbo, b_ty), dbl = make_desc(b_lo + bo, b_lbo, b_sbo, b_ty);
             const uint32_t a_hi = a_col + (uint32_t)ks * 8u, a_lo = a_col + 32u + (uint32_t)ks * 8u;
+            if (ks == BKF / 8 - 1 && it + 1 < total_it) {
+              // the tensor core is busy with this k-block's first MMAs: look whether the NEXT k-block's operands
+              // are there already, so that its MMAs can be queued back to back (same tile only: a new tile
+              // also needs its accumulator buffer)
+              if (kb + 1 < nk) {
+                // (a non-blocking test: stalling here would delay this k-block's commit and with it the
+                // refill of its stage)
+                const uint32_t st2 = (it + 1) & (kStages - 1), ph2 = ((it + 1) / kStages) & 1u;
+                ready = mbar_try(bar(kFullA + st2), ph2) && mbar_try(bar(kFullB + st2), ph2);
+              }
+            }
             tc_mma_ts(d_tmem, a_lo, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
             tc_mma_ts(d_tmem, a_hi, dbl, idesc, 1u);
             tc_mma_ts(d_tmem, a_hi, dbh, idesc, 1u);
           }
           tc_commit(bar(kEmpty + st));  // stage free once these MMAs have read it
           if (kb == nk - 1) tc_commit(bar(kAccFull + buf));
+          trace(launch_flags, 9, it);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== samplers (warps 13-15) ===========================
+    // one exact entry per sampled row and tile, round-to-nearest FP32 FMAs over the RAW operand tiles in
+    // shared memory (A row x B column).  The three warps cover three of the four row quarters, rotating
+    // with the tile ordinal, so every row range of the problem gets sampled.
+    const int slot = warp - 13;
+    uint32_t it = 0, tile_iter = 0;
+    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
+      const uint32_t buf = tile_iter & 1u;
+      const int q = (int)(((uint32_t)slot + tile_iter) & 3u), r = q * 32 + lane;
+      const int scol = (int)(((tile_iter + (uint32_t)q) & 3u) * 32u + (((uint32_t)lane * 7u + tile_iter * 3u) & 31u));
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
+        MBAR_WAIT(kARaw + st, ph);
+        float v[32];
+        {
+          const unsigned char* at = atiles + st * SUB_BYTES;
+          if (LA == kMNFast && TMAA) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + j * 512 + r * 4);
+          } else if (LA == kMNFast) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + b_elem_offset<kMNFast, false>(r, j));
+          } else {
+            const int base = (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(at + base + ((c ^ (r & 7)) << 4));
+              v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+            }
+          }
         }
         __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kARawFree + st));
+        // the raw B tile: complete when the TMA transaction lands (before the lo conversion) or, on the
+        // cp.async path, when the loaders publish the stage
+        if (TMAB) MBAR_WAIT(kTmaFull + st, ph);
+        else MBAR_WAIT(kFullB + st, ph);
+        const unsigned char* bt = tiles + st * STAGE_BYTES;
+        if (launch_flags & kFlagDbgNoSample) {
+        } else if (LB == kMNFast) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            s0 = fmaf(v[j], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j)), s0);
+            s1 = fmaf(v[j + 1], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j + 1)), s1);
+            s2 = fmaf(v[j + 2], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j + 2)), s2);
+            s3 = fmaf(v[j + 3], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j + 3)), s3);
+          }
+        } else {
+          const int base = (scol >> 3) * 1024 + (scol & 7) * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 b = *reinterpret_cast<const float4*>(bt + base + ((c ^ (scol & 7)) << 4));
+            s0 = fmaf(v[4 * c], b.x, s0);
+            s1 = fmaf(v[4 * c + 1], b.y, s1);
+            s2 = fmaf(v[4 * c + 2], b.z, s2);
+            s3 = fmaf(v[4 * c + 3], b.w, s3);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kEmpty + st));  // this warp is done with the B stage
       }
+      MBAR_WAIT(kSmpEmpty + buf, ((tile_iter >> 1) & 1u) ^ 1u);
+      sample[buf * 128 + r] = ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kSmpFull + buf));
     }
   }
 #undef MBAR_WAIT
@@ -795,24 +936,25 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   // ---- teardown + fused stabilize epilogue (sum|C| -> kappa, log-scale, measured truncation bias) ----
   tc_fence_before();
   __syncthreads();
+  if (warp == 12) trace(launch_flags, 30, 0);
   if (warp == 12) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
-  const double bsum = block_sum(local_abs, red);
-  const double bsum_t = FUSED ? block_sum(local_abs_t, red) : 0.0;
-  const double bex = block_sum(s_exact, red);
-  const double btc = block_sum(s_tc, red);
+  double sums[4] = {local_abs, local_abs_t, s_exact, s_tc};
+  block_sum4(sums, red);
+  if (warp == 12) trace(launch_flags, 27, 0);
   if (tid == 0) {
-    d.partials[blockIdx.x] = bsum;
-    d.partials[kMaxPartials + blockIdx.x] = bsum_t;
-    d.partials[2 * kMaxPartials + blockIdx.x] = bex;
-    d.partials[3 * kMaxPartials + blockIdx.x] = btc;
+    d.partials[blockIdx.x] = sums[0];
+    d.partials[kMaxPartials + blockIdx.x] = sums[1];
+    d.partials[2 * kMaxPartials + blockIdx.x] = sums[2];
+    d.partials[3 * kMaxPartials + blockIdx.x] = sums[3];
     __threadfence();
     const uint32_t tk = atomicAdd(&d.tickets[s.ticket], 1u);
     last_block = (tk == gridDim.x - 1);
   }
   __syncthreads();
+  if (warp == 12) trace(launch_flags, 28, 0);
   if (last_block) {
     __threadfence();
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -822,10 +964,9 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       a2 += __ldcg(&d.partials[2 * kMaxPartials + i]);
       a3 += __ldcg(&d.partials[3 * kMaxPartials + i]);
     }
-    const double norm = block_sum(a0, red);
-    const double norm_x = block_sum(a1, red);
-    const double sum_ex = block_sum(a2, red);
-    const double sum_tc = block_sum(a3, red);
+    double tot[4] = {a0, a1, a2, a3};
+    block_sum4(tot, red);
+    const double norm = tot[0], norm_x = tot[1], sum_ex = tot[2], sum_tc = tot[3];
     if (tid == 0) {
       if (FUSED) {
         // the reference stabilises X, then out = X_hat * W: both of its decisions must be "rescale"
@@ -842,6 +983,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       d.tickets[s.ticket] = 0;
     }
   }
+  if (warp == 12) trace(launch_flags, 31, 0);
 }
 
 static int pick_layout4(const GemmMode* rows, int n_rows, const GemmMode* ks, int n_k, bool use_b) {
@@ -891,8 +1033,22 @@ struct TmaShape {
   uint64_t dim[4];
   uint64_t stride[4];  // stride[0] == 1 implied
   uint32_t box[4];
-  bool mn;
+  int swizzle;         // 0 none, 1 SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B
 };
+
+static bool tma_shape_ok(TmaShape& t) {
+  for (int i = 1; i < 4; ++i) {
+    if (t.stride[i] == 0) {
+      if (t.dim[i] != 1) return false;  // broadcast dimension
+      t.stride[i] = 4;
+    }
+    if (t.stride[i] % 4 != 0) return false;  // byte strides must be multiples of 16
+    if ((t.stride[i] * 4) >> 40) return false;
+  }
+  for (int i = 0; i < 4; ++i)
+    if (t.dim[i] == 0 || t.dim[i] > (1ull << 32) || t.box[i] == 0 || t.box[i] > 256) return false;
+  return true;
+}
 
 static bool tma_shape_b(const GemmDev& g, int lb, TmaShape& t) {
   if (g.n_k != 1 || g.K % 4 != 0) return false;
@@ -902,7 +1058,7 @@ static bool tma_shape_b(const GemmDev& g, int lb, TmaShape& t) {
     // innermost N mode contiguous; a tile's npt columns must sit inside it: extent % npt == 0
     if (g.n_n != 1 || g.n[0].sb != 1 || g.n[0].extent % npt != 0 || npt % 32 != 0) return false;
     if (g.n_batch > 1 || (fused && g.n_batch != 0)) return false;
-    t.mn = true;
+    t.swizzle = 2;
     t.dim[0] = 32; t.stride[0] = 1; t.box[0] = 32;
     t.dim[1] = (uint64_t)g.K; t.stride[1] = (uint64_t)g.k[0].sb; t.box[1] = BKF;
     t.dim[2] = (uint64_t)(g.n[0].extent / 32); t.stride[2] = 32; t.box[2] = (uint32_t)(npt / 32);
@@ -915,7 +1071,7 @@ static bool tma_shape_b(const GemmDev& g, int lb, TmaShape& t) {
     }
   } else if (lb == kKFast) {
     if (fused || g.n_n != 1 || g.k[0].sb != 1 || g.n_batch > 1) return false;
-    t.mn = false;
+    t.swizzle = 1;
     t.dim[0] = (uint64_t)g.K; t.stride[0] = 1; t.box[0] = BKF;
     t.dim[1] = (uint64_t)g.n[0].extent; t.stride[1] = (uint64_t)g.n[0].sb; t.box[1] = BN;
     t.dim[2] = g.n_batch ? (uint64_t)g.batch[0].extent : 1;
@@ -925,22 +1081,38 @@ static bool tma_shape_b(const GemmDev& g, int lb, TmaShape& t) {
   } else {
     return false;
   }
-  for (int i = 1; i < 4; ++i) {
-    if (t.stride[i] == 0) {
-      if (t.dim[i] != 1) return false;  // broadcast dimension
-      t.stride[i] = 4;
-    }
-    if (t.stride[i] % 4 != 0) return false;  // byte strides must be multiples of 16
-    if ((t.stride[i] * 4) >> 40) return false;
+  return tma_shape_ok(t);
+}
+
+// The A view (rows = the M group) as a tensor map: raw tile only, read back row-wise by the
+// converter warps, so the layout just has to be conflict-free for them.
+static bool tma_shape_a(const GemmDev& g, int la, TmaShape& t) {
+  if (g.n_k != 1 || g.n_m != 1 || g.n_batch > 1) return false;
+  if (la == kKFast) {
+    if (g.k[0].sa != 1) return false;
+    t.swizzle = 1;  // (32 k, 128 rows): the layout the cp.async path produces
+    t.dim[0] = (uint64_t)g.K; t.stride[0] = 1; t.box[0] = BKF;
+    t.dim[1] = (uint64_t)g.M; t.stride[1] = (uint64_t)g.m[0].sa; t.box[1] = BM;
+  } else if (la == kMNFast) {
+    if (g.m[0].sa != 1) return false;
+    t.swizzle = 0;  // (128 rows, 32 k) -> [k][row], 512-byte lines
+    t.dim[0] = (uint64_t)g.M; t.stride[0] = 1; t.box[0] = BM;
+    t.dim[1] = (uint64_t)g.K; t.stride[1] = (uint64_t)g.k[0].sa; t.box[1] = BKF;
+  } else {
+    return false;
   }
-  return true;
+  t.dim[2] = g.n_batch ? (uint64_t)g.batch[0].extent : 1;
+  t.stride[2] = g.n_batch ? (uint64_t)g.batch[0].sa : 4;
+  t.box[2] = 1;
+  t.dim[3] = 1; t.stride[3] = 4; t.box[3] = 1;
+  return tma_shape_ok(t);
 }
 
 struct TmapKey {
   const void* base;
   uint64_t dim[4], stride[4];
   uint32_t box[4];
-  bool mn;
+  int swizzle;
   bool operator<(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) < 0; }
 };
 
@@ -953,7 +1125,7 @@ static bool get_tensor_map(const TmaShape& t, const void* base, CUtensorMap& out
   memset(&key, 0, sizeof(key));
   key.base = base;
   for (int i = 0; i < 4; ++i) { key.dim[i] = t.dim[i]; key.stride[i] = t.stride[i]; key.box[i] = t.box[i]; }
-  key.mn = t.mn;
+  key.swizzle = t.swizzle;
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { out = it->second; return true; }
@@ -964,7 +1136,9 @@ static bool get_tensor_map(const TmaShape& t, const void* base, CUtensorMap& out
   CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  t.mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  t.swizzle == 2   ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                  : t.swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   if (cache.size() > 8192) cache.clear();
@@ -973,10 +1147,11 @@ static bool get_tensor_map(const TmaShape& t, const void* base, CUtensorMap& out
   return true;
 }
 
-template <int LB, int AMODE, bool FUSED, bool TMAB>
-static cudaError_t launch_one(const ExecCtx& c, const Launch& l, const GemmDev& g, int flags, const CUtensorMap& tmap) {
+template <int LA, int LB, bool FUSED, bool TMAB, bool TMAA>
+static cudaError_t launch_one(const ExecCtx& c, const Launch& l, const GemmDev& g, int flags, const CUtensorMap& tmap_b,
+                              const CUtensorMap& tmap_a) {
   const Plan& p = *c.plan;
-  auto kern = gemm_tf32x3_kernel<LB, AMODE, FUSED, TMAB>;
+  auto kern = gemm_tf32x3_kernel<LA, LB, FUSED, TMAB, TMAA>;
   static AttrOnce attr;  // per instantiation
   {
     cudaError_t e = attr.ensure(kern, p.device, (int)SMEM_BYTES);
@@ -985,25 +1160,47 @@ static cudaError_t launch_one(const ExecCtx& c, const Launch& l, const GemmDev& 
   const int64_t npt = g.fuse_pr ? BN / g.fuse_pr : BN;  // output columns covered by one tile
   const int64_t total = g.B * ((g.M + BM - 1) / BM) * ((g.N + npt - 1) / npt);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(total, p.sm_count));
-  kern<<<grid, kThreadsT, SMEM_BYTES, c.stream>>>(p.d_steps, p.d_gemms, l.first_step, dev_state(c), flags, tmap);
+  kern<<<grid, kThreadsT, SMEM_BYTES, c.stream>>>(p.steps[l.first_step], g, dev_state(c), flags, tmap_b, tmap_a);
   return cudaGetLastError();
 }
 
-template <int LB, int AMODE, bool FUSED>
-static cudaError_t launch_tma(const ExecCtx& c, const Launch& l, const GemmDev& g, int flags, const CUtensorMap& tmap) {
-  if (LB != kAnyLayout && (flags & kFlagTmaB)) return launch_one<LB == kAnyLayout ? kKFast : LB, AMODE, FUSED, true>(c, l, g, flags, tmap);
-  return launch_one<LB, AMODE, FUSED, false>(c, l, g, flags, tmap);
+// TMA variants exist for the 16-byte layouts only: B alone, or A and B (kAnyLayout never carries the flags)
+template <int LA, int LB, bool FUSED>
+static cudaError_t launch_tma(const ExecCtx& c, const Launch& l, const GemmDev& g, int flags, const CUtensorMap& tmap_b,
+                              const CUtensorMap& tmap_a) {
+  constexpr int LBt = LB == kAnyLayout ? kKFast : LB, LAt = LA == kAnyLayout ? kKFast : LA;
+  if (LB != kAnyLayout && (flags & kFlagTmaB)) {
+    if (LA != kAnyLayout && (flags & kFlagTmaA)) return launch_one<LAt, LBt, FUSED, true, true>(c, l, g, flags, tmap_b, tmap_a);
+    return launch_one<LA, LBt, FUSED, true, false>(c, l, g, flags, tmap_b, tmap_a);
+  }
+  return launch_one<LA, LB, FUSED, false, false>(c, l, g, flags, tmap_b, tmap_a);
 }
 
 template <int LB>
-static cudaError_t launch_modes(const ExecCtx& c, const Launch& l, const GemmDev& g, int amode, int flags,
-                                const CUtensorMap& tmap) {
+static cudaError_t launch_modes(const ExecCtx& c, const Launch& l, const GemmDev& g, int la, int flags,
+                                const CUtensorMap& tmap, const CUtensorMap& tmap_a) {
   const bool fused = g.fuse_pr > 0;
-  if (amode == kAVec) return fused ? launch_tma<LB, kAVec, true>(c, l, g, flags, tmap) : launch_tma<LB, kAVec, false>(c, l, g, flags, tmap);
-  return fused ? launch_tma<LB, kAScalar, true>(c, l, g, flags, tmap) : launch_tma<LB, kAScalar, false>(c, l, g, flags, tmap);
+#define CTN_T32_LA(LA_)                                                                                  \
+  if (la == LA_)                                                                                         \
+    return fused ? launch_tma<LA_, LB, true>(c, l, g, flags, tmap, tmap_a) : launch_tma<LA_, LB, false>(c, l, g, flags, tmap, tmap_a);
+  CTN_T32_LA(kKFast)
+  CTN_T32_LA(kMNFast)
+  CTN_T32_LA(kAnyLayout)
+#undef CTN_T32_LA
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace t32
+
+// Debug aid (not part of the documented ABI): copy out and clear CTA 0's event time line
+// ([event][ordinal] SM clocks, 0 = not recorded).
+extern "C" int ctn_debug_t32_trace(long long* host_out, int cap) {
+  const int n = std::min(cap, t32::kTraceEvents * t32::kTraceIts);
+  if (cudaMemcpyFromSymbol(host_out, t32::g_trace, (size_t)n * sizeof(long long)) != cudaSuccess) return -1;
+  static long long zeros[t32::kTraceEvents * t32::kTraceIts];
+  cudaMemcpyToSymbol(t32::g_trace, zeros, sizeof(zeros));
+  return n;
+}
 
 bool gemm_tf32_supported(const Plan& p, const StepDev& s, const GemmDev& g) {
   if (p.dtype != CTN_F32) return false;
@@ -1016,49 +1213,53 @@ bool gemm_tf32_supported(const Plan& p, const StepDev& s, const GemmDev& g) {
   return true;
 }
 
-// cfg 8 = this kernel.  la carries the A load mode, lb the B staging layout; fuse_pad bit 0 says the
-// output can be written with 16-byte stores (subject to the pointer's alignment at launch).
+// cfg 8 = this kernel.  la / lb are the staging layouts of A and B; fuse_pad bit 0 says the output
+// can be written with 16-byte stores (subject to the pointer's alignment at launch).
 void gemm_tf32_configure(const Plan&, GemmDev& g) {
   using namespace t32;
   g.cfg = 8;
   g.splits = 1;
-  bool a_vec = g.n_k == 1 && g.k[0].sa == 1, batch_ok_b = true, c_vec = g.fuse_pr == 0 && g.n_n > 0;
+  bool batch_ok_a = true, batch_ok_b = true, c_vec = g.fuse_pr == 0 && g.n_n > 0;
   for (int i = 0; i < g.n_batch; ++i) {
-    a_vec = a_vec && !(g.batch[i].sa & 3);
+    batch_ok_a = batch_ok_a && !(g.batch[i].sa & 3);
     batch_ok_b = batch_ok_b && !(g.batch[i].sb & 3);
     c_vec = c_vec && !(g.batch[i].sc & 3);
   }
-  for (int i = 0; i < g.n_m; ++i) {
-    a_vec = a_vec && !(g.m[i].sa & 3);
-    c_vec = c_vec && !(g.m[i].sc & 3);
-  }
+  for (int i = 0; i < g.n_m; ++i) c_vec = c_vec && !(g.m[i].sc & 3);
   for (int i = 0; i < g.n_n; ++i) {
     if (i == g.n_n - 1) c_vec = c_vec && g.n[i].sc == 1 && (g.n[i].extent % 4 == 0);
     else c_vec = c_vec && !(g.n[i].sc & 3);
   }
-  g.la = a_vec ? kAVec : kAScalar;
+  g.la = batch_ok_a ? pick_layout4(g.m, g.n_m, g.k, g.n_k, false) : kAnyLayout;
   g.lb = batch_ok_b ? pick_layout4(g.n, g.n_n, g.k, g.n_k, true) : kAnyLayout;
   g.fuse_pad = c_vec ? 1 : 0;
   g.scratch_off = 0;
 }
 
 cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, bool b_aligned, bool c_aligned,
-                             const void* b_ptr) {
+                             const void* b_ptr, const void* a_ptr) {
   using namespace t32;
   const Plan& p = *c.plan;
   const StepDev& s = p.steps[l.first_step];
   const GemmDev& g = p.gemms[s.gemm_off];
-  const int amode = a_aligned ? g.la : kAScalar, lb = b_aligned ? g.lb : kAnyLayout;
+  const int la = a_aligned ? g.la : kAnyLayout, lb = b_aligned ? g.lb : kAnyLayout;
   int flags = (g.fuse_pad & 1) && c_aligned ? kFlagCVec : 0;
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_a;
   memset(&tmap, 0, sizeof(tmap));
+  memset(&tmap_a, 0, sizeof(tmap_a));
   static const bool no_tma = getenv("CTN_TF32_NO_TMA") != nullptr;
   TmaShape shape;
-  if (!no_tma && b_aligned && tma_shape_b(g, lb, shape) && get_tensor_map(shape, b_ptr, tmap)) flags |= kFlagTmaB;
+  if (!no_tma && b_aligned && tma_shape_b(g, lb, shape) && get_tensor_map(shape, b_ptr, tmap)) {
+    flags |= kFlagTmaB;
+    static const bool no_tma_a = getenv("CTN_TF32_NO_TMA_A") != nullptr;
+    if (!no_tma_a && a_aligned && tma_shape_a(g, la, shape) && get_tensor_map(shape, a_ptr, tmap_a)) flags |= kFlagTmaA;
+  }
+  static const int dbg = getenv("CTN_T32_DEBUG") ? atoi(getenv("CTN_T32_DEBUG")) & (kFlagDbgNoSample | kFlagDbgNoLo | kFlagTrace) : 0;
+  flags |= dbg;
   switch (lb) {
-    case kKFast: return launch_modes<kKFast>(c, l, g, amode, flags, tmap);
-    case kMNFast: return launch_modes<kMNFast>(c, l, g, amode, flags, tmap);
-    default: return launch_modes<kAnyLayout>(c, l, g, amode, flags, tmap);
+    case kKFast: return launch_modes<kKFast>(c, l, g, la, flags, tmap, tmap_a);
+    case kMNFast: return launch_modes<kMNFast>(c, l, g, la, flags, tmap, tmap_a);
+    default: return launch_modes<kAnyLayout>(c, l, g, la, flags, tmap, tmap_a);
   }
 }
 

@@ -1032,7 +1032,7 @@ static int execute_impl(const ctn_plan* plan, const void* const* operands, void*
         const int cfg = p.gemms[gs.gemm_off].cfg;
         if (cfg == 3 || cfg == 4) e = launch_skinny(ctx, l);
         else if (p.dtype != CTN_F32) e = launch_gemm(ctx, l, a_al, b_al);
-        else if (cfg == 8) e = launch_gemm_tf32(ctx, l, a_al, b_al, ((uintptr_t)ptrs[gs.out_slot] & 15) == 0, ptrs[gs.in_slot[1]]);
+        else if (cfg == 8) e = launch_gemm_tf32(ctx, l, a_al, b_al, ((uintptr_t)ptrs[gs.out_slot] & 15) == 0, ptrs[gs.in_slot[1]], ptrs[gs.in_slot[0]]);
         else e = launch_gemm_tf32_v1(ctx, l, a_al, b_al);
         break;
       }

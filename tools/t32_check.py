@@ -37,6 +37,10 @@ CASES = [
     ("akb,kc->abc", [(40, 64, 52), (64, 72)], None, False),        # 18 summed mode mid-tensor in A
     ("aklb,klc->abc", [(24, 8, 8, 20), (8, 8, 72)], None, False),  # 19 two summed modes
     ("ab,cb->ac", [(2048, 4096), (2048, 4096)], None, True),       # 20 long K
+    ("br,prs,bp,qst,bq->bt", [(4096, 512), (2, 512, 512), (4096, 2), (2, 512, 512), (4096, 2)],
+     ((0, 1), (0, 3), (0, 2), (0, 1)), True),                      # 21 two cfg 3 sites: M-fast intermediate
+    ("ab,cb->ac", [(128, 32), (128, 32)], None, True),             # 22 one tile, one k-block: fixed cost of a launch
+    ("ab,cb->ac", [(128 * 148, 512), (128, 512)], None, True),     # 23 one tile per CTA, 16 k-blocks
 ]
 
 
@@ -49,7 +53,12 @@ def run(idx):
     print(idx, einstr, shapes, plan.launch_kinds, end=" ... ", flush=True)
     t0 = time.time()
     T, c, fl = plan.execute_host(ops)
-    want = np.einsum(einstr, *[o.astype(np.float64) for o in ops])
+    if timed:  # big case: float64 reference on the GPU (the CPU einsum takes most of a minute)
+        import torch
+
+        want = torch.einsum(einstr, *[torch.as_tensor(o).cuda().double() for o in ops]).cpu().numpy()
+    else:
+        want = np.einsum(einstr, *[o.astype(np.float64) for o in ops], optimize=True)
     kappa = np.abs(want).mean()
     err_T = np.abs(T.astype(np.float64) / (want / kappa) - 1).max()
     err_c = c - np.log(kappa)

@@ -1,0 +1,49 @@
+"""Time line of one CTA of the tcgen05 kernel (CTN_T32_DEBUG=16): per k-block, when each pipeline event
+happened on SM 0 (cycles relative to the kernel's start).  python tools/t32_trace.py <t32_check case>"""
+import ctypes, os, sys
+import numpy as np
+os.environ["CTN_T32_DEBUG"] = "16"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from contractn_b200 import engine, planner
+import t32_check
+import torch
+
+idx = int(sys.argv[1])
+einstr, shapes, path, _ = t32_check.CASES[idx]
+rng = np.random.default_rng(idx)
+ops = [torch.as_tensor(rng.uniform(0.1, 1.0, s).astype(np.float32)).cuda() for s in shapes]
+lst = planner.contract_path(einstr, *shapes, optimize=path if path is not None else "auto")[1]
+plan = engine.Plan(lst, shapes, np.float32)
+lib = engine.load_library()
+E, I = 32, 1024
+buf = (ctypes.c_longlong * (E * I))()
+for _ in range(3):
+    plan.execute_device(ops)
+torch.cuda.synchronize()
+lib.ctn_debug_t32_trace(buf, E * I)  # drop the warm-up records
+plan.execute_device(ops)
+torch.cuda.synchronize()
+lib.ctn_debug_t32_trace(buf, E * I)
+t = np.array(buf[:], dtype=np.int64).reshape(E, I)
+names = {0: "start", 1: "A raw landed", 2: "A tmem free", 3: "FullA", 4: "issued", 5: "B landed", 6: "FullB",
+         7: "mma: A ready", 8: "mma: B ready", 9: "mma issued", 10: "epi: acc full", 12: "epi: tile done",
+         20: "loader setup done", 30: "all roles done", 31: "end"}
+# (with several gemm launches in the plan the LAST launch's records survive)
+t0 = t[0, 0]
+cols = [21, 22, 23, 24, 4, 1, 2, 3, 5, 6, 7, 8, 9]
+names.update({21: "i:A free", 22: "i:A copies", 23: "i:A arrive", 24: "i:B free", 13: "epi: ld0", 14: "epi: ld1", 15: "epi: ld2",
+              16: "epi: ld3", 17: "epi: table ready", 27: "block sums done", 28: "ticket done"})
+n_it = int((t[9] > 0).sum())
+print(f"k-blocks recorded: {n_it}; span start->end {t[31, 0] - t0} cycles")
+print("it    " + " ".join(f"{names[c][:12]:>12}" for c in cols))
+show = list(range(min(n_it, 40))) + ([] if n_it <= 44 else list(range(n_it - 4, n_it)))
+for it in show:
+    print(f"{it:4d}  " + " ".join(f"{int(t[c, it] - t0):12d}" if t[c, it] > 0 else " " * 12 for c in cols))
+for c in (20, 17, 10, 13, 14, 15, 16, 12, 30, 27, 28, 31):
+    for it in range(8):
+        if t[c, it] > 0:
+            print(f"   {names[c]:>18} [{it}] at {int(t[c, it] - t0)}")
+d = np.diff(t[9, :n_it])
+if len(d) > 4:
+    print("cycles between consecutive 'mma issued': median", int(np.median(d)), "mean", int(d.mean()))
