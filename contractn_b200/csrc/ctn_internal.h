@@ -96,7 +96,10 @@ struct StateHdr {
   int32_t flags;      // CTN_RESULT_*
   int32_t chain_exp;  // global exponent of the last tracked chain
   double chain_mean;  // its mean |value| relative to 2^chain_exp
-  double reserved;
+  double reserved;    // diagnostics of a timed-out pipeline wait (gemm_tf32.cu)
+  double final_abs;   // sum |entries| of the tensor the LAST recorded step leaves after its rescale: numel when it
+                      // was rescaled (mean |T| = 1), its raw norm when it was not (einsum.py:102); read by the
+                      // multi-GPU merge (ctn_merge_batch_shards_peer) straight from the state block
 };
 
 struct StateLayout {
@@ -194,9 +197,10 @@ struct PtrChunk {
 cudaError_t launch_init_state(const Plan& plan, char* ws, cudaStream_t stream, const void* const* slot_ptrs);
 constexpr int kDotMaxOut = 16;          // dot kernel: at most this many outputs ...
 constexpr int64_t kDotMinK = 1 << 15;   // ... each a sum over at least this many terms
-constexpr int kShardStatBlocks = 148;  // CTN_SHARD_STATS_WORDS = 3 + kShardStatBlocks + 1 doubles
-cudaError_t launch_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws,
-                               cudaStream_t stream);
+constexpr int kMailboxMaxWorld = 64;   // ranks per peer mailbox (CTN_MAILBOX_WORDS = 2 * 4 * kMailboxMaxWorld doubles)
+cudaError_t launch_merge_shards_peer(void* data, int64_t numel, int dtype, const StateHdr* hdr, double* const* mailboxes,
+                                     int world, int rank, unsigned long long seq, double* log_scale_out,
+                                     cudaStream_t stream);
 cudaError_t launch_merge_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                                 double* log_scale_out, cudaStream_t stream);
 cudaError_t launch_generic(const ExecCtx& c, const Launch& l);

@@ -83,6 +83,7 @@ __device__ __forceinline__ void record_scale(const DevState& d, int slot, double
   const double kappa = norm / (double)numel;
   d.kappa[slot] = rescale ? kappa : 1.0;
   d.inv_kappa[slot] = rescale ? 1.0 / kappa : 1.0;
+  d.hdr->final_abs = rescale ? (double)numel : norm;
   if (rescale) d.hdr->log_scale += log(kappa);
 }
 

@@ -28,13 +28,14 @@
 // Shared memory: 4 x (B_hi 16 KB + B_lo 16 KB) + 4 x A_raw 16 KB + offset tables = 197 KB.
 //
 // Accumulator truncation.  The tensor core truncates (round toward zero) every time it adds into
-// its FP32 accumulator: a systematic relative bias of ~6e-8 per MMA in the chain, common to all
-// entries.  It cancels in the normalised mantissa T-hat but would land in the log-scale.  The kernel
-// MEASURES it: warps 13-15 evaluate ONE entry per row for three of the four row quarters of every
-// tile (rotating) with round-to-nearest FP32 FMAs (unbiased; four independent partial sums) over the
-// raw fp32 operand tiles in shared memory; the epilogue compares these samples with
-// what the tensor core produced, and the last CTA adds ln(sum|exact| / sum|tensor core|) to the
-// log-scale register.  Unbiased by construction, data independent, off the producers' critical path.
+// its FP32 accumulator: a systematic relative bias of ~6e-8 per MMA in the chain (1.2e-5 at K = 512).
+// Its mean would land in the log-scale, and it differs by a few percent between rows of different
+// magnitude -- a difference that persists from step to step and drifts the mantissas of a 510-step
+// sweep by 1e-4.  The kernel therefore makes every ROW SUM of every tile exact: the A-converter warps
+// publish the per-k column sums of the raw B tile, warps 13-15 form sum_k A[m,k] * colsum[k] in
+// float64 from the raw A rows (= the exact sum over the tile's columns of row m), the epilogue sums
+// the row as the tensor core produced it and rescales the row by the ratio before storing.
+// Data independent, no model of the hardware's rounding, off the producers' critical path.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -62,13 +63,13 @@ constexpr uint32_t kAStageCol0 = 256;  // A stages: 64 columns each (hi 32 | lo 
 // mbarrier indices
 constexpr int kFullA = 0, kFullB = kFullA + kStages, kEmpty = kFullB + kStages, kTmaFull = kEmpty + kStages,
               kARaw = kTmaFull + kStages, kARawFree = kARaw + kStages, kAccFull = kARawFree + kStages, kAccEmpty = kAccFull + 2, kSmpFull = kAccEmpty + 2,
-              kSmpEmpty = kSmpFull + 2, kNumBars = kSmpEmpty + 2;
-static_assert(kNumBars <= 32, "barrier block is 32 words");
+              kSmpEmpty = kSmpFull + 2, kBsum = kSmpEmpty + 2, kNumBars = kBsum + kStages;
+static_assert(kNumBars <= 40, "barrier block is 40 words");
 
 constexpr int A_OFF = kStages * STAGE_BYTES;  // raw A stages follow the B stages
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)kStages * (STAGE_BYTES + SUB_BYTES) +
-                              5 * 128 * sizeof(int64_t) + 2 * 128 * sizeof(double) + 32 * sizeof(uint64_t) + 64 +
-                              72 * sizeof(double);
+                              5 * 128 * sizeof(int64_t) + 2 * 128 * sizeof(double) + 40 * sizeof(uint64_t) + 64 +
+                              72 * sizeof(double) + kStages * 4 * 32 * sizeof(float);
 
 enum : int32_t { kKFast = 0, kMNFast = 1, kAnyLayout = 2 };  // B staging layouts
 enum : int32_t { kFlagCVec = 1, kFlagTmaB = 2, kFlagTmaA = 32, // launch flags
@@ -367,9 +368,10 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   int64_t* colC = rowtab + 256;                                                               // [128]    epilogue
   double* sample = reinterpret_cast<double*>(colC + 128);                                     // [2][128] exact entries
   uint64_t* bars = reinterpret_cast<uint64_t*>(sample + 2 * 128);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 4);
   double* red = reinterpret_cast<double*>(tmem_slot + 16);
+  float* bsum = reinterpret_cast<float*>(red + 72);  // [kStages][4 warps][32 k]: column sums of the raw B tile
   __shared__ bool last_block;
 
   const float* A = (const float*)d.ptrs[s.in_slot[0]];
@@ -396,16 +398,17 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     for (int st = 0; st < kStages; ++st) {
       mbar_init(bar(kFullA + st), 4);    // one elected lane per A-producer warp
       mbar_init(bar(kFullB + st), 4);    // one elected lane per B-producer warp
-      mbar_init(bar(kEmpty + st), 4);    // tcgen05.commit + the three sampling warps
+      mbar_init(bar(kEmpty + st), 8);    // tcgen05.commit + the three sampling warps + the four column-sum warps
       mbar_init(bar(kTmaFull + st), 1);  // TMA: one arrive.expect_tx + the transaction bytes
       mbar_init(bar(kARaw + st), TMAA ? 1 : kRoleThreads);  // TMA transaction / cp.async completion of every loader thread
       mbar_init(bar(kARawFree + st), 7);         // one elected lane per A-converter warp and per sampler warp
+      mbar_init(bar(kBsum + st), 4);             // column sums of the B tile published by the A-converter warps
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kAccFull + b), 1);
       mbar_init(bar(kAccEmpty + b), 4);
       mbar_init(bar(kSmpFull + b), 3);
-      mbar_init(bar(kSmpEmpty + b), 3);
+      mbar_init(bar(kSmpEmpty + b), 4);
     }
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -423,7 +426,6 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   if (warp == 12) trace(launch_flags, 0, 0);
 
   double local_abs = 0.0, local_abs_t = 0.0;  // sum|out| and (fused) sum|X|         (epilogue threads)
-  double s_exact = 0.0, s_tc = 0.0;           // sampled entries: exact vs tensor core (epilogue threads)
 
   if (warp < 4) {
     // =========================== A converters ===========================
@@ -478,12 +480,50 @@ __global__ void __launch_bounds__(kThreadsT, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kFullA + st));
         if (warp == 0) trace(launch_flags, 3, it);
+        // ---- column sums of the raw B tile, per k (for the exact row sums of the samplers): thread r takes
+        // column r's 32 k-values; a halving butterfly leaves lane l with the warp's sum for k = bitrev5(l) ----
+        if (TMAB) MBAR_WAIT(kTmaFull + st, ph);
+        else MBAR_WAIT(kFullB + st, ph);
+        {
+          const unsigned char* bt = tiles + st * STAGE_BYTES;
+          float bv[32];
+          if (LB == kMNFast) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bv[j] = *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(r, j));
+          } else {
+            const int base = (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(bt + base + ((c ^ (r & 7)) << 4));
+              bv[4 * c] = x.x; bv[4 * c + 1] = x.y; bv[4 * c + 2] = x.z; bv[4 * c + 3] = x.w;
+            }
+          }
+          // step with half-width h: lanes whose bit h is clear keep the lower h entries, the others the upper h
+#pragma unroll
+          for (int h = 16; h >= 1; h >>= 1) {
+            const bool up = (lane & h) != 0;
+#pragma unroll
+            for (int j = 0; j < h; ++j) {
+              const float send = up ? bv[j] : bv[j + h];
+              const float keep = up ? bv[j + h] : bv[j];
+              bv[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            }
+          }
+          // lane l now holds k = sum over set bits: bit 4 of l -> +16, bit 3 -> +8, ... (entry index built msb first)
+          const int kidx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+          bsum[(st * 4 + warp) * 32 + kidx] = bv[0];
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(kBsum + st));
+          mbar_arrive(bar(kEmpty + st));  // this warp is done with the B stage
+        }
       }
     }
   } else if (warp < 8) {
     // =========================== epilogue ===========================
     const int q = warp - 4, r = q * 32 + lane, te = tid - kRoleThreads;
-    const float alpha = (float)(d.inv_kappa[s.in_slot[0]] * d.inv_kappa[s.in_slot[1]]);
+    const float alpha0 = (float)(d.inv_kappa[s.in_slot[0]] * d.inv_kappa[s.in_slot[1]]);
     const float* Wp = FUSED ? (const float*)d.ptrs[s.in_slot[2]] : nullptr;
     const float alpha_w = FUSED ? (float)d.inv_kappa[s.in_slot[2]] : 0.f;
     const bool c_vec = (launch_flags & kFlagCVec) != 0;
@@ -524,8 +564,33 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       if (q == 0) trace(launch_flags, 10, tile_iter);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol0 + buf * 128u;
-      const int schunk = (int)((tile_iter + (uint32_t)q) & 3u), sidx = (int)(((uint32_t)lane * 7u + tile_iter * 3u) & 31u);
-      float tcval = 0.f, lf = 0.f, lt = 0.f;
+      // ---- pass 1: this row's sum over the tile as the tensor core produced it; with the samplers' exact row
+      // sum it gives the row's accumulator-truncation factor, applied to every entry of the row below ----
+      double rs = 0.0, rs_abs = 0.0;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t a[32];
+        tc_ld32(tbase + (uint32_t)cc * 32u, a);
+        tc_ld_wait();
+        float part = 0.f, part_abs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          part += __uint_as_float(a[j]);
+          part_abs += fabsf(__uint_as_float(a[j]));
+        }
+        rs += (double)part;
+        rs_abs += (double)part_abs;
+      }
+      MBAR_WAIT(kSmpFull + buf, (tile_iter >> 1) & 1u);
+      const double ex = sample[buf * 128 + r];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kSmpEmpty + buf));
+      // the ratio is well conditioned only when the row does not cancel (same-sign data: |sum| = sum|.|); a row of
+      // mixed signs is left alone (its truncation errors are not a common factor anyway)
+      double rho = (fabs(rs) > 0.5 * rs_abs && ex != 0.0) ? ex / rs : 1.0;
+      if (!(fabs(rho - 1.0) < 1e-3)) rho = 1.0;
+      const float alpha = (float)((double)alpha0 * rho);
+      float lf = 0.f, lt = 0.f;
       float* Crow = C + oc + (lin ? (int64_t)tc.tn * npt * scn : 0);
       // (rows / columns outside the problem were zero-filled on the way in, so their accumulator entries are
       // exact zeros: the sums below need no predicate, only the stores do)
@@ -541,10 +606,6 @@ __global__ void __launch_bounds__(kThreadsT, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(kAccEmpty + buf));
-          }
-          if (cc == schunk) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tcval = (j == sidx) ? __uint_as_float(a[j]) : tcval;
           }
           if (row_ok) {
             if (c_vec) {
@@ -588,10 +649,6 @@ __global__ void __launch_bounds__(kThreadsT, 1)
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(kAccEmpty + buf));
             }
-            if (cc == schunk) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) tcval = (j == sidx) ? __uint_as_float(a[j]) : tcval;
-            }
             // rows / columns outside the problem were zero-filled, so their entries are exact zeros
             const float wv = rr == 0 ? wv4[0] : rr == 1 ? wv4[1] : rr == 2 ? wv4[2] : wv4[3];
 #pragma unroll
@@ -615,14 +672,6 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       local_abs += (double)lf;
       local_abs_t += (double)lt;
       if (q == 0) trace(launch_flags, 12, tile_iter);
-      if ((((uint32_t)q - tile_iter) & 3u) != 3u) {  // this quarter's rows are sampled in this tile (see the samplers)
-        MBAR_WAIT(kSmpFull + buf, (tile_iter >> 1) & 1u);
-        const double ex = sample[buf * 128 + r];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kSmpEmpty + buf));
-        s_exact += fabs(ex);
-        s_tc += fabs((double)tcval);
-      }
     }
   } else if (warp < 12) {
     // =========================== loaders (A and B) + B converters ===========================
@@ -864,69 +913,68 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     __syncwarp();
   } else {
     // =========================== samplers (warps 13-15) ===========================
-    // one exact entry per sampled row and tile, round-to-nearest FP32 FMAs over the RAW operand tiles in
-    // shared memory (A row x B column).  The three warps cover three of the four row quarters, rotating
-    // with the tile ordinal, so every row range of the problem gets sampled.
-    const int slot = warp - 13;
+    // EXACT row sums of the tile, sum_n X[m, n] = sum_k A[m, k] * (sum_n B[k, n]), round-to-nearest FMAs over the raw
+    // A rows (shared memory) and the B column sums published by the A-converter warps.  96 threads cover the
+    // 128 rows: thread i takes row i, the first 32 also row 96 + i.
+    const int i0 = (warp - 13) * 32 + lane;
+    const bool two = warp == 13;  // (uniform per warp)
     uint32_t it = 0, tile_iter = 0;
     for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
       const uint32_t buf = tile_iter & 1u;
-      const int q = (int)(((uint32_t)slot + tile_iter) & 3u), r = q * 32 + lane;
-      const int scol = (int)(((tile_iter + (uint32_t)q) & 3u) * 32u + (((uint32_t)lane * 7u + tile_iter * 3u) & 31u));
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      double acc_a = 0.0, acc_b = 0.0;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
         MBAR_WAIT(kARaw + st, ph);
-        float v[32];
+        float va[32], vb[32];
         {
           const unsigned char* at = atiles + st * SUB_BYTES;
-          if (LA == kMNFast && TMAA) {
+          auto read_row = [&](int r, float (&v)[32]) {
+            if (LA == kMNFast && TMAA) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + j * 512 + r * 4);
-          } else if (LA == kMNFast) {
+              for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + j * 512 + r * 4);
+            } else if (LA == kMNFast) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + b_elem_offset<kMNFast, false>(r, j));
-          } else {
-            const int base = (r >> 3) * 1024 + (r & 7) * 128;
+              for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + b_elem_offset<kMNFast, false>(r, j));
+            } else {
+              const int base = (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(at + base + ((c ^ (r & 7)) << 4));
-              v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+              for (int c = 0; c < 8; ++c) {
+                const float4 x = *reinterpret_cast<const float4*>(at + base + ((c ^ (r & 7)) << 4));
+                v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+              }
             }
-          }
+          };
+          read_row(i0, va);
+          if (two) read_row(96 + i0, vb);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kARawFree + st));
-        // the raw B tile: complete when the TMA transaction lands (before the lo conversion) or, on the
-        // cp.async path, when the loaders publish the stage
-        if (TMAB) MBAR_WAIT(kTmaFull + st, ph);
-        else MBAR_WAIT(kFullB + st, ph);
-        const unsigned char* bt = tiles + st * STAGE_BYTES;
-        if (launch_flags & kFlagDbgNoSample) {
-        } else if (LB == kMNFast) {
+        MBAR_WAIT(kBsum + st, ph);
+        const float* bp = bsum + st * 4 * 32;
+        const float bs = (bp[lane] + bp[32 + lane]) + (bp[64 + lane] + bp[96 + lane]);  // column sum for k = lane
+        if (!(launch_flags & kFlagDbgNoSample)) {
+          // 32 terms per k-block in round-to-nearest FP32 FMAs (four independent chains; ~1e-7 relative, zero
+          // mean), the k-blocks added in float64: a dependent chain of 32 float64 FMAs per k-block made these
+          // warps the slowest stage of the pipeline
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            s0 = fmaf(v[j], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j)), s0);
-            s1 = fmaf(v[j + 1], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j + 1)), s1);
-            s2 = fmaf(v[j + 2], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j + 2)), s2);
-            s3 = fmaf(v[j + 3], *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(scol, j + 3)), s3);
+            const float b0 = __shfl_sync(0xffffffffu, bs, j), b1 = __shfl_sync(0xffffffffu, bs, j + 1);
+            const float b2 = __shfl_sync(0xffffffffu, bs, j + 2), b3 = __shfl_sync(0xffffffffu, bs, j + 3);
+            p0 = fmaf(va[j], b0, p0); p1 = fmaf(va[j + 1], b1, p1); p2 = fmaf(va[j + 2], b2, p2); p3 = fmaf(va[j + 3], b3, p3);
+            if (two) {
+              q0 = fmaf(vb[j], b0, q0); q1 = fmaf(vb[j + 1], b1, q1); q2 = fmaf(vb[j + 2], b2, q2); q3 = fmaf(vb[j + 3], b3, q3);
+            }
           }
-        } else {
-          const int base = (scol >> 3) * 1024 + (scol & 7) * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 b = *reinterpret_cast<const float4*>(bt + base + ((c ^ (scol & 7)) << 4));
-            s0 = fmaf(v[4 * c], b.x, s0);
-            s1 = fmaf(v[4 * c + 1], b.y, s1);
-            s2 = fmaf(v[4 * c + 2], b.z, s2);
-            s3 = fmaf(v[4 * c + 3], b.w, s3);
-          }
+          acc_a += (double)((p0 + p1) + (p2 + p3));
+          if (two) acc_b += (double)((q0 + q1) + (q2 + q3));
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kEmpty + st));  // this warp is done with the B stage
+        if (lane == 0) mbar_arrive(bar(kEmpty + st));  // done with this stage's column sums
       }
       MBAR_WAIT(kSmpEmpty + buf, ((tile_iter >> 1) & 1u) ^ 1u);
-      sample[buf * 128 + r] = ((double)s0 + (double)s1) + ((double)s2 + (double)s3);
+      sample[buf * 128 + i0] = acc_a;
+      if (two) sample[buf * 128 + 96 + i0] = acc_b;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kSmpFull + buf));
     }
@@ -941,7 +989,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
-  double sums[4] = {local_abs, local_abs_t, s_exact, s_tc};
+  double sums[4] = {local_abs, local_abs_t, 0.0, 0.0};
   block_sum4(sums, red);
   if (warp == 12) trace(launch_flags, 27, 0);
   if (tid == 0) {
@@ -966,7 +1014,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     }
     double tot[4] = {a0, a1, a2, a3};
     block_sum4(tot, red);
-    const double norm = tot[0], norm_x = tot[1], sum_ex = tot[2], sum_tc = tot[3];
+    const double norm = tot[0], norm_x = tot[1];
     if (tid == 0) {
       if (FUSED) {
         // the reference stabilises X, then out = X_hat * W: both of its decisions must be "rescale"
@@ -975,11 +1023,6 @@ __global__ void __launch_bounds__(kThreadsT, 1)
         if (!(norm_x > kMinNorm) || !(norm / kappa_x > kMinNorm)) d.hdr->flags |= CTN_RESULT_DEGENERATE;
       }
       record_scale(d, s.out_slot, norm, s.out_numel);
-      // measured accumulator-truncation bias: stored = true * (sum_tc / sum_ex), a pure gauge factor
-      if (sum_tc > 0.0 && sum_ex > 0.0) {
-        const double rho = sum_ex / sum_tc;
-        if (fabs(rho - 1.0) < 1e-3) d.hdr->log_scale += log(rho);
-      }
       d.tickets[s.ticket] = 0;
     }
   }

@@ -35,6 +35,7 @@ __global__ void init_state_kernel(DevState d, int n_slots, int n_tickets, int ch
       d.hdr->chain_exp = 0;
       d.hdr->chain_mean = 1.0;
       d.hdr->reserved = 0.0;
+      d.hdr->final_abs = 0.0;
     }
     for (int i = t; i < n_tickets; i += stride) d.tickets[i] = 0u;
     for (int i = t; i < n_slots; i += stride) {
@@ -881,6 +882,7 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
         const double kappa = rescale ? 1.0 / inv : 1.0;
         d.kappa[s.out_slot] = kappa;
         d.inv_kappa[s.out_slot] = inv;
+        if (s.is_final) d.hdr->final_abs = rescale ? numel_d : norm;
         if (rescale) log_acc += log(kappa);
       }
     } else {
@@ -898,6 +900,7 @@ __global__ void __launch_bounds__(kInterpWarps * 32) interp_kernel(const StepDev
         d.kappa[s.out_slot] = rescale ? kappa : 1.0;
         d.inv_kappa[s.out_slot] = inv;
         inv_s[li] = inv;
+        if (s.is_final) d.hdr->final_abs = rescale ? (double)s.out_numel : norm;
         if (rescale) log_acc += log(kappa);
       }
       __threadfence_block();
@@ -972,44 +975,86 @@ __global__ void __launch_bounds__(kThreads) merge_shards_kernel(T* data, int64_t
   if (blockIdx.x == 0 && threadIdx.x == 0) *log_scale_out = c_star + log(kappa);
 }
 
-// (log-scale, sum|T|, numel) of one shard in ONE launch: per-block partials in ws[3..3+grid), the last block
-// (ticket in ws[kShardStatBlocks+3], left at zero again) adds them in block order -> same bits every run.
-template <typename T>
-__global__ void __launch_bounds__(kThreads) shard_stats_kernel(const T* __restrict__ data, int64_t numel,
-                                                               const double* __restrict__ log_scale, double* ws) {
-  double s = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride) s += fabs((double)data[i]);
-  __shared__ double red[33];
-  __shared__ bool last;
-  s = block_sum(s, red);
-  unsigned* ticket = reinterpret_cast<unsigned*>(ws + 3 + kShardStatBlocks);
-  if (threadIdx.x == 0) {
-    ws[3 + blockIdx.x] = s;
-    __threadfence();
-    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) tot += ((volatile double*)ws)[3 + b];
-    ws[0] = *log_scale;
-    ws[1] = tot;
-    ws[2] = (double)numel;
-    *ticket = 0u;
-  }
+// ---------------------------------------------------------------------------
+// multi-GPU: the whole merge of batch shards in ONE kernel, no host-launched collective.  Every rank
+// posts its (log-scale, sum|T_shard|, numel_shard) triple -- read straight from the plan's state block
+// -- into slot `rank` of every peer's mailbox (peer-mapped device memory, stores over NVLink), then
+// waits until all `world` slots of its OWN mailbox carry this call's sequence number, recomputes the
+// global scale in a fixed order (same bits on every rank) and rescales its shard in place.
+// Mailbox: [2 parities][world][4 doubles] = (c, abs, numel, seq); a rank can be at most one call ahead
+// of a peer (it needs the peer's post of call k to finish call k), so two parities suffice.
+// ---------------------------------------------------------------------------
+struct PeerBoxes {
+  double* p[kMailboxMaxWorld];
+};
+
+__device__ __forceinline__ void st_release_sys(double* p, double v) {
+  asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_acquire_sys(const double* p) {
+  double v;
+  asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
 }
 
-cudaError_t launch_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws,
-                               cudaStream_t stream) {
-  const int grid =
-      (int)std::max<int64_t>(1, std::min<int64_t>((numel + kThreads * 8 - 1) / (kThreads * 8), kShardStatBlocks));
+template <typename T>
+__global__ void __launch_bounds__(kThreads) merge_shards_peer_kernel(T* data, int64_t numel, const StateHdr* __restrict__ hdr,
+                                                                     PeerBoxes boxes, int world, int rank,
+                                                                     unsigned long long seq, double* log_scale_out) {
+  __shared__ double tab[3 * kMailboxMaxWorld];
+  __shared__ int give_up;
+  const int par = (int)(seq & 1ull);
+  const double seq_d = (double)seq;  // exact below 2^53
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    // post my triple into slot `rank` of peer threadIdx.x's mailbox: payload, then the flag with release order
+    double* slot = boxes.p[threadIdx.x] + ((size_t)par * world + rank) * 4;
+    slot[0] = hdr->log_scale;
+    slot[1] = hdr->final_abs;
+    slot[2] = (double)numel;
+    __threadfence_system();
+    st_release_sys(slot + 3, seq_d);
+  }
+  if (threadIdx.x == 0) give_up = 0;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const double* slot = boxes.p[rank] + ((size_t)par * world + threadIdx.x) * 4;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(slot + 3) != seq_d) {
+      if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer never arrived; do not hang the GPU
+        give_up = 1;
+        break;
+      }
+    }
+    tab[3 * threadIdx.x] = slot[0];
+    tab[3 * threadIdx.x + 1] = slot[1];
+    tab[3 * threadIdx.x + 2] = slot[2];
+  }
+  __syncthreads();
+  double c_star = -INFINITY;
+  for (int i = 0; i < world; ++i) c_star = fmax(c_star, tab[3 * i]);
+  double S = 0.0, N = 0.0;
+  for (int i = 0; i < world; ++i) {  // fixed order: every rank computes the same bits
+    S += tab[3 * i + 1] * exp(tab[3 * i] - c_star);
+    N += tab[3 * i + 2];
+  }
+  const double kappa = S / N;
+  const double scale = give_up ? __longlong_as_double(0x7ff8000000000000LL) : exp(tab[3 * rank] - c_star) / kappa;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += stride)
+    data[i] = (T)((double)data[i] * scale);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *log_scale_out = give_up ? scale : c_star + log(kappa);
+}
+
+cudaError_t launch_merge_shards_peer(void* data, int64_t numel, int dtype, const StateHdr* hdr, double* const* mailboxes,
+                                     int world, int rank, unsigned long long seq, double* log_scale_out,
+                                     cudaStream_t stream) {
+  PeerBoxes boxes;
+  for (int i = 0; i < kMailboxMaxWorld; ++i) boxes.p[i] = i < world ? mailboxes[i] : nullptr;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((numel + kThreads - 1) / kThreads, 148 * 8));
   if (dtype == CTN_F32)
-    shard_stats_kernel<float><<<grid, kThreads, 0, stream>>>((const float*)data, numel, log_scale, ws);
+    merge_shards_peer_kernel<float><<<grid, kThreads, 0, stream>>>((float*)data, numel, hdr, boxes, world, rank, seq, log_scale_out);
   else
-    shard_stats_kernel<double><<<grid, kThreads, 0, stream>>>((const double*)data, numel, log_scale, ws);
+    merge_shards_peer_kernel<double><<<grid, kThreads, 0, stream>>>((double*)data, numel, hdr, boxes, world, rank, seq, log_scale_out);
   return cudaGetLastError();
 }
 
@@ -1290,6 +1335,7 @@ __global__ void __launch_bounds__(kThreads) chain_kernel(const StepDev* __restri
       const double mean = S / (double)numel;
       d.hdr->chain_exp = E;
       d.hdr->chain_mean = fine ? mean : 1.0;
+      d.hdr->final_abs = (double)numel;  // the materialise pass leaves mean |T| = 1 (a degenerate run is re-executed)
       if (fine) d.hdr->log_scale += E * M_LN2 + log(mean);
       else d.hdr->flags |= CTN_RESULT_DEGENERATE;
       d.kappa[s.out_slot] = 1.0;      // the materialise pass leaves a normalised tensor

@@ -1070,13 +1070,19 @@ int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, vo
   return rc;
 }
 
-int ctn_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws, void* stream) {
-  static_assert(CTN_SHARD_STATS_WORDS == 3 + kShardStatBlocks + 1, "header constant out of date");
-  if (!data || !log_scale || !ws || numel < 0) return CTN_ERR_INVALID;
+int ctn_merge_batch_shards_peer(void* data, int64_t numel, int dtype, const void* workspace, double* const* mailboxes,
+                                int world, int rank, uint64_t seq, double* log_scale_out, void* stream) {
+  static_assert(CTN_MAILBOX_WORDS == 2 * 4 * kMailboxMaxWorld, "header constant out of date");
+  if (!data || !workspace || !mailboxes || !log_scale_out || numel < 0) return CTN_ERR_INVALID;
+  if (world < 1 || world > kMailboxMaxWorld || rank < 0 || rank >= world || seq == 0) return CTN_ERR_INVALID;
   if (dtype != CTN_F32 && dtype != CTN_F64) return CTN_ERR_UNSUPPORTED;
-  cudaError_t e = launch_shard_stats(data, numel, dtype, log_scale, ws, (cudaStream_t)stream);
+  for (int i = 0; i < world; ++i)
+    if (!mailboxes[i]) return CTN_ERR_INVALID;
+  // the state header sits at the start of every plan's workspace (StateLayout::hdr == 0)
+  cudaError_t e = launch_merge_shards_peer(data, numel, dtype, (const StateHdr*)workspace, mailboxes, world, rank,
+                                           (unsigned long long)seq, log_scale_out, (cudaStream_t)stream);
   if (e != cudaSuccess) {
-    set_cuda_error(e, "shard_stats launch");
+    set_cuda_error(e, "merge_shards_peer launch");
     return CTN_ERR_CUDA;
   }
   return CTN_OK;

@@ -42,11 +42,11 @@ EXPORTS = (
     "ctn_plan_output_rank", "ctn_plan_output_extents", "ctn_plan_output_numel",
     "ctn_plan_num_launches", "ctn_plan_flops", "ctn_plan_step_bytes",
     "ctn_plan_launch_kind", "ctn_plan_describe", "ctn_plan_execute", "ctn_plan_execute_timed", "ctn_plan_execute_host",
-    "ctn_shard_stats", "ctn_merge_batch_shards", "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
+    "ctn_merge_batch_shards_peer", "ctn_merge_batch_shards", "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
 )
 
 
-CTN_SHARD_STATS_WORDS = 152  # include/ctn_b200.h
+CTN_MAILBOX_WORDS = 512  # include/ctn_b200.h
 
 
 class EngineError(RuntimeError):
@@ -123,8 +123,9 @@ def load_library():
         lib.ctn_plan_execute_host.argtypes = [vp, ctypes.POINTER(vp), vp, ctypes.POINTER(dbl),
                                               ctypes.POINTER(i32), ctypes.c_int]
         lib.ctn_plan_execute_host.restype = ctypes.c_int
-        lib.ctn_shard_stats.argtypes = [vp, i64, ctypes.c_int, vp, vp, vp]
-        lib.ctn_shard_stats.restype = ctypes.c_int
+        lib.ctn_merge_batch_shards_peer.argtypes = [vp, i64, ctypes.c_int, vp, ctypes.POINTER(vp), ctypes.c_int,
+                                                    ctypes.c_int, ctypes.c_uint64, vp, vp]
+        lib.ctn_merge_batch_shards_peer.restype = ctypes.c_int
         lib.ctn_merge_batch_shards.argtypes = [vp, i64, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, vp]
         lib.ctn_merge_batch_shards.restype = ctypes.c_int
         lib.ctn_status_string.argtypes = [ctypes.c_int]
@@ -273,30 +274,59 @@ class Plan:
 
         device = tensors[0].device
         # the plan's descriptor tables live on the device that was current when it was created
-        # (get_plan keys on it); launches go to that device whatever the caller's current one is
-        with self._lock, torch.cuda.device(device):
+        # (get_plan keys on it); launches go to that device whatever the caller's current one is.
+        # (torch.cuda.device() as a context manager costs ~0.1 ms per call: only switch when needed)
+        prev = torch.cuda.current_device()
+        switch = device.index is not None and prev != device.index
+        if switch:
+            torch.cuda.set_device(device)
+        try:
+            with self._lock:
+                return self._execute_device_locked(tensors, device, out, out_mode, stream, timed)
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
+
+    def _execute_device_locked(self, tensors, device, out, out_mode, stream, timed):
+        import torch
+
+        _, _ws, ws_ptr, tail = self._device_scratch(device)
+        tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
+        if out is None:
+            out = torch.empty(self.out_shape, dtype=tdtype, device=device)
+        n = len(self.shapes)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        if stream is None:
+            stream = torch.cuda.current_stream(device).cuda_stream
+        if timed:
+            ms = (ctypes.c_float * max(1, self.num_launches))()
+            _check(
+                self._lib.ctn_plan_execute_timed(self._h, ptrs, out.data_ptr(), tail.data_ptr(),
+                                                 tail.data_ptr() + 8, ws_ptr, out_mode, stream, ms),
+                "ctn_plan_execute_timed",
+            )
+            return out, tail, [float(ms[i]) for i in range(self.num_launches)]
+        _check(
+            self._lib.ctn_plan_execute(self._h, ptrs, out.data_ptr(), tail.data_ptr(), tail.data_ptr() + 8,
+                                       ws_ptr, out_mode, stream),
+            "ctn_plan_execute",
+        )
+        return out, tail
+
+    def bind(self, tensors, out=None, out_mode=CTN_OUT_SPLIT):
+        """Pre-resolve everything a device-resident call needs (operand pointers, output, workspace) so
+        that repeated executions on the SAME resident operands cost one ctypes call each -- collecting 100
+        ``data_ptr()`` values per call is otherwise as expensive as the 0.3 ms cfg-2 step itself.  The
+        operands are kept alive by the returned object; their contents may change between runs."""
+        import torch
+
+        device = tensors[0].device
+        with torch.cuda.device(device):
             _, _ws, ws_ptr, tail = self._device_scratch(device)
             tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
             if out is None:
                 out = torch.empty(self.out_shape, dtype=tdtype, device=device)
-            n = len(self.shapes)
-            ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
-            if stream is None:
-                stream = torch.cuda.current_stream(device).cuda_stream
-            if timed:
-                ms = (ctypes.c_float * max(1, self.num_launches))()
-                _check(
-                    self._lib.ctn_plan_execute_timed(self._h, ptrs, out.data_ptr(), tail.data_ptr(),
-                                                     tail.data_ptr() + 8, ws_ptr, out_mode, stream, ms),
-                    "ctn_plan_execute_timed",
-                )
-                return out, tail, [float(ms[i]) for i in range(self.num_launches)]
-            _check(
-                self._lib.ctn_plan_execute(self._h, ptrs, out.data_ptr(), tail.data_ptr(), tail.data_ptr() + 8,
-                                           ws_ptr, out_mode, stream),
-                "ctn_plan_execute",
-            )
-            return out, tail
+        return BoundCall(self, list(tensors), out, tail, ws_ptr, out_mode, device)
 
     def describe(self):
         """What the plan compiler decided: one line per launch."""
@@ -309,6 +339,27 @@ class Plan:
         # fused chains (any dtype) and fused GEMM+consumer steps (float32) can flag a degenerate norm
         fused = "chain" in self.launch_kinds or (self.dtype == np.float32 and "gemm" in self.launch_kinds)
         return fused and not (self.flags & CTN_PLAN_EXACT_STEPS)
+
+
+class BoundCall:
+    """A plan bound to resident operands (see :meth:`Plan.bind`).  ``run()`` enqueues one execution on
+    torch's current stream and returns ``(out, tail)`` -- the same buffers every time."""
+
+    def __init__(self, plan, tensors, out, tail, ws_ptr, out_mode, device):
+        self.plan, self.tensors, self.out, self.tail = plan, tensors, out, tail
+        self._ptrs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        self._args = (plan._h, self._ptrs, out.data_ptr(), tail.data_ptr(), tail.data_ptr() + 8, ws_ptr, out_mode)
+        self._device = device
+        self._fn = plan._lib.ctn_plan_execute
+
+    def run(self, stream=None):
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+        with self.plan._lock:
+            _check(self._fn(*self._args, stream), "ctn_plan_execute")
+        return self.out, self.tail
 
 
 # ---------------------------------------------------------------------------
@@ -454,7 +505,8 @@ def _run_torch(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
         if flags & CTN_RESULT_DEGENERATE:
             exact = get_plan(contraction_list, shapes, ndt, strides=strides, flags=CTN_PLAN_EXACT_STEPS, device=dev)
             out, tail = exact.execute_device(tensors, out_mode=out_mode)
-    return out, tail[0].to(tdt)
+    # (a copy: `tail` is the plan's own output slot and is overwritten by its next execution)
+    return out, tail[0].to(tdt, copy=True)
 
 
 def core_contract(operands, contract_list, backend=None, **einsum_kwargs):

@@ -6,9 +6,9 @@ path shards naturally:
 * **batch sharding** -- independent network evaluations along a batch hub are
   split across ranks; each rank contracts its shard to a split-format pair
   ``(T_r, c_r)`` with its OWN scale, and :func:`merge_batch_shards` restores the
-  reference's single global scale after one 24-byte-per-rank all-gather (the
-  output stays sharded; on CUDA the scalar algebra and the rescale are two
-  kernels of the engine, ``ctn_shard_stats`` and ``ctn_merge_batch_shards``).
+  reference's single global scale (the output stays sharded).  On CUDA the whole
+  merge is ONE kernel, ``ctn_merge_batch_shards_peer``: the ranks' 24-byte
+  triples travel through peer-mapped mailboxes over NVLink, no NCCL call.
 * **bond slicing** -- the largest contracted bonds are fixed to one value per
   slice, slices are distributed round-robin, every rank accumulates its slices
   with a log-sum-exp merge and :func:`merge_slice_sums` all-reduces the
@@ -22,6 +22,7 @@ CPU tensors over gloo (the latter is how the logic is tested without GPUs).
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -31,49 +32,92 @@ def _world(group=None):
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
-_SHARD_BUFFERS = {}
+_PEER = {}       # (device index, world, group id) -> peer mailbox state, or False when unavailable
+_TABLES = {}
 
 
-def _shard_buffers(dev, world):
-    """Per-device scratch of the CUDA merge (reused in stream order; the stats ticket must start at zero)."""
-    key = (dev.index, world)
-    if key not in _SHARD_BUFFERS:
-        from .engine import CTN_SHARD_STATS_WORDS
+def _peer_state(dev, world, group):
+    """Peer-mapped mailboxes for the one-kernel merge: one CTN_MAILBOX_WORDS buffer per rank in symmetric
+    memory (``torch.distributed._symmetric_memory``: cuMem handles exchanged once, then plain device
+    pointers over NVLink).  Returns None when symmetric memory cannot be set up (then NCCL is used)."""
+    key = (dev.index, world, id(group))
+    st = _PEER.get(key)
+    if st is None:
+        st = False
+        if os.environ.get("CTN_NO_PEER_MERGE") is None:
+            try:
+                import ctypes
 
-        _SHARD_BUFFERS[key] = (torch.zeros(CTN_SHARD_STATS_WORDS, dtype=torch.float64, device=dev),
-                               torch.empty(world * 3, dtype=torch.float64, device=dev))
-    return _SHARD_BUFFERS[key]
+                import torch.distributed._symmetric_memory as symm
+
+                from .engine import CTN_MAILBOX_WORDS
+
+                grp = group if group is not None else dist.group.WORLD
+                box = symm.empty(CTN_MAILBOX_WORDS, dtype=torch.float64, device=dev)
+                box.zero_()
+                hdl = symm.rendezvous(box, grp)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                assert len(ptrs) == world and all(ptrs)
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=group)  # every mailbox is zeroed before anybody posts
+                st = {"box": box, "hdl": hdl, "ptrs": (ctypes.c_void_p * world)(*ptrs), "seq": 0,
+                      "c_out": torch.empty(1, dtype=torch.float64, device=dev)}
+            except Exception as exc:  # no symmetric memory on this platform / build
+                import warnings
+
+                warnings.warn(f"peer mailbox merge unavailable ({type(exc).__name__}: {exc}); using an NCCL all-gather")
+                st = False
+        _PEER[key] = st
+    return st or None
 
 
-def merge_batch_shards(T_local, c_local, group=None):
+def merge_batch_shards(T_local, c_local, group=None, plan=None):
     """Global split-format pair for a batch-sharded evaluation.
 
     ``T_local`` is this rank's shard of the output, ``c_local`` its log-scale: a
     0-d/1-element float64 tensor (only element 0 is read).  Returns
     ``(T_shard, c)`` with ONE log-scale ``c`` shared by all ranks such that the
     concatenation of the shards has mean-abs 1, exactly what the reference
-    returns for the unsharded network.  One small all-gather (3 doubles per
-    rank) is the only communication.
+    returns for the unsharded network.
+
+    CUDA, with the :class:`~contractn_b200.engine.Plan` that just produced ``T_local``: ONE kernel
+    (``ctn_merge_batch_shards_peer``) exchanges the ranks' (log-scale, sum|T|, numel) triples through
+    peer-mapped mailboxes over NVLink and rescales the shard -- no host-launched collective, the triple
+    comes from the plan's own state block.  Otherwise: one small all-gather (3 doubles per rank).
     """
     if _world(group) == 1:
         return T_local, c_local.reshape(-1)[:1].to(torch.float64)
     world = _world(group)
     if T_local.is_cuda and T_local.is_contiguous() and T_local.dtype in (torch.float32, torch.float64) \
             and c_local.dtype == torch.float64:
-        # three launches in all: stats kernel -> NCCL all-gather of 24 B per rank -> merge kernel
         from . import engine
 
         lib = engine.load_library()
         dev = T_local.device
-        ws, table = _shard_buffers(dev, world)
         stream = torch.cuda.current_stream(dev).cuda_stream
         dt = engine.CTN_F32 if T_local.dtype == torch.float32 else engine.CTN_F64
-        engine._check(lib.ctn_shard_stats(T_local.data_ptr(), T_local.numel(), dt, c_local.data_ptr(),
-                                          ws.data_ptr(), stream), "ctn_shard_stats")
-        dist.all_gather_into_tensor(table, ws[:3], group=group)
+        rank = dist.get_rank(group)
+        ws_ptr = plan._dev[2] if plan is not None and getattr(plan, "_dev", None) is not None else None
+        peer = _peer_state(dev, world, group) if ws_ptr is not None else None
+        if peer is not None:
+            peer["seq"] += 1
+            engine._check(lib.ctn_merge_batch_shards_peer(T_local.data_ptr(), T_local.numel(), dt, ws_ptr, peer["ptrs"],
+                                                          world, rank, peer["seq"], peer["c_out"].data_ptr(), stream),
+                          "ctn_merge_batch_shards_peer")
+            return T_local, peer["c_out"]
+        # NCCL path: all-gather of 24 B per rank, then the rescale kernel
+        key = (dev.index, world)
+        if key not in _TABLES:
+            _TABLES[key] = (torch.empty(world * 3, dtype=torch.float64, device=dev),
+                            torch.empty(3, dtype=torch.float64, device=dev))
+        table, mine = _TABLES[key]
+        mine[0] = c_local.reshape(-1)[0]
+        mine[1] = torch.linalg.vector_norm(T_local.reshape(-1), ord=1).to(torch.float64)
+        mine[2] = float(T_local.numel())
+        dist.all_gather_into_tensor(table, mine, group=group)
         c_out = torch.empty(1, dtype=torch.float64, device=dev)
         engine._check(lib.ctn_merge_batch_shards(T_local.data_ptr(), T_local.numel(), dt, table.data_ptr(), world,
-                                                 dist.get_rank(group), c_out.data_ptr(), stream),
+                                                 rank, c_out.data_ptr(), stream),
                       "ctn_merge_batch_shards")
         return T_local, c_out
     c_local = c_local.reshape(-1)[0].to(torch.float64)
@@ -257,3 +301,52 @@ def contract_sliced(einstr, *operands, slice_labels=None, min_slices=None, optim
     if split_format:
         return T, c
     return T * torch.exp(c).to(T.dtype)
+
+
+# ---------------------------------------------------------------------------
+# output-slab sharding (cfg 4: the output is far bigger than the operands)
+# ---------------------------------------------------------------------------
+def slab_bounds(extent, rank, world):
+    """Contiguous, near-equal split of an open index of size ``extent``."""
+    return rank * extent // world, (rank + 1) * extent // world
+
+
+def contract_output_slabs(einstr, *operands, label=None, optimize="auto", group=None, contract_fn=None,
+                          merge_fn=None):
+    """``contract(..., split_format=True)`` with ONE OPEN index split across the ranks of ``group``.
+
+    An output entry depends only on the operand rows with the same value of an open index, so every rank
+    contracts the network with that index restricted to its slab -- views of the operands, no copies, no
+    exchange of tensor data -- and keeps its slab of the result: a CP reconstruction whose output (550 GB
+    at BASELINE's literal size) fits no single GPU is held slab-wise (cfg 4).  The
+    split-format pair needs ONE global scale: the same 24-byte exchange as for batch shards
+    (:func:`merge_batch_shards`).  Returns ``(T_slab, c, (lo, hi))``; ``label`` defaults to the first
+    output index.  Contracted-rank slicing would need an all-reduce of the whole output instead.
+    """
+    from .engine import contract as engine_contract
+
+    contract_fn = contract_fn or engine_contract
+    terms, out = _parse(einstr)
+    if not out:
+        raise ValueError("the network has no open index to shard")
+    label = label or out[0]
+    if label not in out:
+        raise ValueError(f"{label!r} is not an output index of {einstr!r}")
+    world = _world(group)
+    rank = dist.get_rank(group) if world > 1 else 0
+    extent = max(op.shape[t.index(label)] for t, op in zip(terms, operands) if label in t)
+    lo, hi = slab_bounds(int(extent), rank, world)
+    sliced = []
+    for t, op in zip(terms, operands):
+        if label in t:
+            sel = tuple(slice(lo, hi) if c == label else slice(None) for c in t)
+            op = op[sel]
+        sliced.append(op)
+    res = contract_fn(einstr, *sliced, optimize=optimize, split_format=True)
+    T = torch.as_tensor(res[0])
+    c = torch.as_tensor(res[1], dtype=torch.float64, device=T.device).reshape(1)
+    if merge_fn is not None:
+        T, c = merge_fn(T, c)
+    else:
+        T, c = merge_batch_shards(T, c, group=group)
+    return T, c, (lo, hi)

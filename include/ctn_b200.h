@@ -167,20 +167,26 @@ int ctn_plan_execute_timed(const ctn_plan* plan, const void* const* operands, vo
 int ctn_plan_execute_host(ctn_plan* plan, const void* const* operands_host, void* out_host,
                           double* log_scale_host, int32_t* flags_host, int out_mode);
 
-/* Batch-sharded evaluations, step 1: this rank's (log-scale, sum|T_shard|, numel_shard) triple in one
- * kernel.  `ws` is CTN_SHARD_STATS_WORDS doubles of device memory, ZERO before the first use (the
- * kernel leaves its ticket word at zero again); ws[0..2] is the triple to all-gather, the rest is
- * scratch.  sum|T| is measured, not assumed = numel: a shard under the reference's 1e-7 threshold
- * is returned unscaled (contractn/einsum.py:102). */
-#define CTN_SHARD_STATS_WORDS 152
-int ctn_shard_stats(const void* data, int64_t numel, int dtype, const double* log_scale, double* ws, void* stream);
-
-/* Batch-sharded evaluations, step 2 (one process per GPU): bring this rank's shard of the split-format
- * result to the GLOBAL scale.  `table` is the all-gathered [world][3] array of
- * (log-scale, sum|T_shard|, numel_shard) per rank (device memory); the kernel rescales `data` in
- * place by exp(c_rank - c*) / kappa and writes the common log-scale c* + ln(kappa) to *log_scale_out,
- * where c* = max_i c_i and kappa = sum_i(abs_i * exp(c_i - c*)) / sum_i numel_i -- the reference's
- * single global scale for the unsharded tensor (contractn/einsum.py:89-107). */
+/* Batch-sharded evaluations (one process per GPU): bring this rank's shard of the split-format result
+ * to the GLOBAL scale, i.e. the reference's single scale for the unsharded tensor
+ * (contractn/einsum.py:89-107 applied to the concatenation of the shards).
+ *
+ * ctn_merge_batch_shards_peer does the whole merge in ONE kernel and without a host-launched
+ * collective: `workspace` is the workspace of the ctn_plan_execute call that produced `data` (its
+ * state block holds this shard's log-scale and sum|T_shard|); `mailboxes[i]` is rank i's mailbox,
+ * CTN_MAILBOX_WORDS doubles of ZEROED device memory mapped into this process (peer access over
+ * NVLink; mailboxes[rank] is local).  The kernel posts this rank's (log-scale, sum|T|, numel)
+ * triple into every peer's mailbox, waits for all `world` triples of call number `seq` (1, 2, 3 ...
+ * -- the same on every rank, incremented per call), and rescales `data` in place by
+ * exp(c_rank - c*) / kappa, writing the common log-scale c* + ln(kappa) to *log_scale_out, where
+ * c* = max_i c_i and kappa = sum_i(abs_i * exp(c_i - c*)) / sum_i numel_i.  world <= 64.
+ *
+ * ctn_merge_batch_shards is the second half alone, for callers that gathered the [world][3] table
+ * of triples themselves (e.g. with an all-gather). */
+#define CTN_MAILBOX_WORDS 512
+int ctn_merge_batch_shards_peer(void* data, int64_t numel, int dtype, const void* workspace,
+                                double* const* mailboxes, int world, int rank, uint64_t seq,
+                                double* log_scale_out, void* stream);
 int ctn_merge_batch_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                            double* log_scale_out, void* stream);
 

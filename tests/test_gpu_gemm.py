@@ -143,11 +143,10 @@ def test_gemm_step_f32(gpu_engine, einstr, shapes, what):
     ops64 = [o.astype(np.float64) for o in ops]
     want_T, want_c = oracle.core_contract(ops64, lst)
     np.testing.assert_allclose(T.astype(np.float64), want_T, rtol=1e-5, err_msg=what)
-    # log-scale: the tensor core truncates when adding into its FP32 accumulator, a
-    # bias of ~6e-8 per chained add that is common to all entries (so it cancels in
-    # the mantissa T) but shows in the scale; chains are K/24 adds long
-    k_len = max(int(np.prod([d for d, ch in zip(shapes[0], einstr.split(",")[0]) if ch not in einstr.split("->")[1]])), 1)
-    assert abs(float(c) - float(want_c)) < max(1e-5, 5e-9 * k_len)
+    # log-scale: the tensor core truncates when adding into its FP32 accumulator (~6e-8 per chained
+    # add, common to all entries); the kernel measures that bias on sampled entries and removes it
+    # from the log-scale, so one step is good to float32 rounding
+    assert abs(float(c) - float(want_c)) < 2e-6
 
 
 def test_tf32_kernel_is_selected_and_accurate_for_long_k(gpu_engine):
@@ -202,7 +201,7 @@ def test_fused_consumer_f32(gpu_engine, einstr, shapes, path, what):
     assert fl == 0
     want_T, want_c = oracle.core_contract([o.astype(np.float64) for o in ops], lst)
     np.testing.assert_allclose(T.astype(np.float64), want_T, rtol=1e-5, err_msg=what)
-    assert abs(float(c) - float(want_c)) < 2e-5
+    assert abs(float(c) - float(want_c)) < 2e-6
     # and the unfused plan agrees
     exact = gpu_engine.Plan(lst, shapes, np.float32, flags=gpu_engine.CTN_PLAN_EXACT_STEPS)
     assert exact.launch_kinds == ("gemm", "generic", "finalize")

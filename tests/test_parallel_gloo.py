@@ -102,6 +102,24 @@ def test_slicing_with_open_indices():
         assert abs(c - want_c) < 1e-9
 
 
+def _slab_case(rank, world):
+    rng = np.random.default_rng(7)
+    # CP reconstruction "ba,ca,da->bcd" (cfg 4): slab over the first open index
+    einstr = "ba,ca,da->bcd"
+    ops = [rng.uniform(0, 1, (9, 5)), rng.uniform(0, 1, (7, 5)), rng.uniform(0, 1, (6, 5))]
+    T, c, (lo, hi) = parallel.contract_output_slabs(einstr, *ops, contract_fn=_oracle_contract)
+    T2, c2, (lo2, hi2) = parallel.contract_output_slabs(einstr, *ops, label="c", contract_fn=_oracle_contract)
+    want_T, want_c = _oracle_contract(einstr, *ops)
+    return T.numpy(), float(c[0]), want_T[lo:hi], T2.numpy(), float(c2[0]), want_T[:, lo2:hi2], float(want_c)
+
+
+def test_output_slab_sharding_keeps_the_global_scale():
+    for T, c, want_T, T2, c2, want_T2, want_c in _run(_slab_case):
+        np.testing.assert_allclose(T, want_T, rtol=1e-12)
+        np.testing.assert_allclose(T2, want_T2, rtol=1e-12)
+        assert abs(c - want_c) < 1e-9 and abs(c2 - want_c) < 1e-9
+
+
 def test_sliced_network_bookkeeping():
     net = parallel.SlicedNetwork("abc,bd,cde->ae", [(5, 6, 7), (6, 8), (7, 8, 3)], ("d", "b"))
     assert net.einstr == "ac,,ce->ae"
