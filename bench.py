@@ -384,6 +384,117 @@ def run_config(name, peaks, hbm_peak, with_cpu):
     return rec
 
 
+def run_multi_gpu_records(world, rank, dev):
+    """N > 1 only: the two OTHER ways the path shards, measured on this job's GPUs.
+
+    * ``slab``  -- cfg 4 CP reconstruction with the first open index split across the ranks (output-slab
+      sharding: no tensor data is exchanged, one 24-byte scale exchange).  Tier M (I = R = 1024) at N = 2, 4;
+      the literal tier L (I = 4096, R = 1024: 550 GB of output, 68.7 GB per GPU) at N = 8.
+    * ``sliced`` -- cfg 5 at its parity tier (closed 8x8 grid, D = 8) with the most expensive bond sliced
+      (8 slices round-robin over the ranks, log-sum-exp merge of the slice sums), timed against the UNSLICED
+      contraction on one GPU: a bond lives in the boundary for only L of the L^2 sweep steps, so slicing
+      multiplies the total work -- the ratio reported is the honest one.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from contractn_b200 import engine, networks, parallel, planner
+
+    def timed(fn, reps=2):
+        best, res = None, None
+        for _ in range(reps):
+            res = None  # (release the previous result first: a tier-L slab is 68.7 GB)
+            torch.cuda.empty_cache()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item()) if best is None else min(best, float(t.item()))
+        return best, res
+
+    out = {}
+    # ---------------- slab sharding (cfg 4) ----------------
+    try:
+        I, R = (4096, 1024) if world >= 8 else (1024, 1024)
+        tn, opt = networks.cp_tn(I, R)
+        einstr = tn.einsum_str
+        fs = [torch.as_tensor(p).to(dev) for p in tn.params]
+        sec, (T, c, (lo, hi)) = timed(lambda: parallel.contract_output_slabs(einstr, *fs, optimize=opt))
+        rng = np.random.default_rng(40 + rank)
+        idx = np.stack([rng.integers(lo, hi, 2000), rng.integers(0, I, 2000), rng.integers(0, I, 2000)], axis=1)
+        terms = einstr.split("->")[0].split(",")
+        got = T[idx[:, 0] - lo, idx[:, 1], idx[:, 2]].cpu().numpy() * math.exp(float(c[0]))
+        # the defining sum (entry (i, j, k) depends on rows i, j, k of the factors in output-index order)
+        outl = einstr.split("->")[1]
+        facs = [tn.params[[t[0] for t in terms].index(l)] for l in outl]
+        want = np.einsum("na,na,na->n", facs[0][idx[:, 0]], facs[1][idx[:, 1]], facs[2][idx[:, 2]])
+        err = torch.tensor([float(np.abs(got / want - 1).max())], dtype=torch.float64, device=dev)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        flops = 2.0 * I * I * I * R + I * I * R
+        rec = {"workload": f"cfg4 CP I={I} R={R} f64, output slabs over index '{outl[0]}' on {world} GPUs",
+               "tier": "L (literal, 550 GB output)" if I == 4096 else "M", "seconds": sec,
+               "aggregate_path_tflops": flops / sec / 1e12, "slab_GB_per_gpu": T.numel() * 8 / 1e9,
+               "max_rel_err_sampled_entries": float(err.item()), "samples_per_rank": 2000}
+        del T
+        torch.cuda.empty_cache()
+        if I == 1024:
+            dist.barrier()
+            if rank == 0:
+                lst = planner.cached_contract_list(einstr, tuple(tuple(f.shape) for f in fs), optimize=opt)
+                plan = engine.get_plan(lst, tuple(tuple(f.shape) for f in fs), np.float64, device=dev.index)
+                b = plan.bind(fs)
+                b.run()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                b.run()
+                torch.cuda.synchronize()
+                one = time.perf_counter() - t0
+                rec["seconds_unsharded_1gpu"] = one
+                rec["speedup_vs_unsharded_1gpu"] = one / sec
+                del b, plan
+                engine.clear_plan_cache()
+                torch.cuda.empty_cache()
+            dist.barrier()
+        out["slab"] = rec
+    except Exception as exc:
+        out["slab"] = {"error": f"{type(exc).__name__}: {exc}"}
+    # ---------------- bond slicing (cfg 5) ----------------
+    try:
+        tn, path = networks.peps_tn(8, 8)
+        einstr = tn.einsum_str
+        ops = [torch.as_tensor(p).to(dev) for p in tn.params]
+        shapes = tuple(tuple(o.shape) for o in ops)
+        lst = planner.cached_contract_list(einstr, shapes, optimize=path)
+        labels = parallel.choose_slice_labels(einstr, shapes, lst, 8)
+        sec, (Ts, cs) = timed(lambda: parallel.contract_sliced(einstr, *ops, slice_labels=labels, optimize=path,
+                                                                split_format=True))
+        rec = {"workload": "cfg5 parity tier: closed 8x8 grid, D = 8, f64; 8 slices of one bond, round-robin over "
+                           f"{world} GPUs", "seconds": sec}
+        if rank == 0:
+            plan = engine.get_plan(lst, shapes, np.float64, device=dev.index)
+            b = plan.bind(ops)
+            b.run()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, tail = b.run()
+            torch.cuda.synchronize()
+            one = time.perf_counter() - t0
+            net = parallel.SlicedNetwork(einstr, shapes, labels)
+            lst_s = planner.cached_contract_list(net.einstr, net.shapes, optimize=path)
+            rec.update({"seconds_unsliced_1gpu": one, "speedup_vs_unsliced_1gpu": one / sec,
+                        "work_multiplier_of_slicing": net.n_slices * planner.path_flops(lst_s, net.einstr, net.shapes)
+                        / planner.path_flops(lst, einstr, shapes),
+                        "abs_err_log_scale_vs_unsliced": abs(float(cs[0]) - float(tail[0].item()))})
+        dist.barrier()
+        out["sliced"] = rec
+    except Exception as exc:
+        out["sliced"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -488,6 +599,11 @@ def main():
     h2d = int(sum(a.nbytes for a in arrays))
     d2h = int(T.nbytes + 16)
 
+    multi = None
+    if world > 1 and args.configs != "none":
+        del dev_ops, bound
+        torch.cuda.empty_cache()
+        multi = run_multi_gpu_records(world, rank, dev)
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         kinds = plan.launch_kinds
@@ -526,8 +642,10 @@ def main():
             line["cpu_baseline"] = {"value": 1.0 / best, "unit": "contractions/s", "cores": host_threads(),
                                     "kind": "port", "sample": "full cfg2 workload, best of 2 contractions",
                                     "seconds_per_contraction": best}
+        if multi is not None:
+            line["multi_gpu"] = multi
         if world == 1 and args.configs != "none":
-            del dev_ops
+            del dev_ops, bound
             torch.cuda.empty_cache()
             peaks = cublas_peaks()
             peaks["hbm_gbs"] = hbm_peak
