@@ -5,7 +5,7 @@
 // 3xTF32 error-compensated split (lo*hi + hi*lo + hi*hi, FP32 accumulation in TMEM) so that float32
 // results stay at sgemm-class accuracy (north_star: rtol 1e-5; one-pass TF32 gives 7e-5 per step).
 //
-// Warp-specialised, persistent over 128 x 128 output tiles, one CTA (16 warps) per SM:
+// Warp-specialised, persistent over 128 x 128 output tiles, one CTA (13 warps) per SM:
 //
 //   warps 8-11  loaders + B converters.  They stage BOTH raw operand tiles in shared memory, three
 //               k-blocks ahead, with a cursor that runs across tile boundaries: A by cp.async (16 B
@@ -31,11 +31,12 @@
 // its FP32 accumulator: a systematic relative bias of ~6e-8 per MMA in the chain (1.2e-5 at K = 512).
 // Its mean would land in the log-scale, and it differs by a few percent between rows of different
 // magnitude -- a difference that persists from step to step and drifts the mantissas of a 510-step
-// sweep by 1e-4.  The kernel therefore makes every ROW SUM of every tile exact: the A-converter warps
-// publish the per-k column sums of the raw B tile, warps 13-15 form sum_k A[m,k] * colsum[k] in
-// float64 from the raw A rows (= the exact sum over the tile's columns of row m), the epilogue sums
-// the row as the tensor core produced it and rescales the row by the ratio before storing.
-// Data independent, no model of the hardware's rounding, off the producers' critical path.
+// sweep by 1e-4.  The kernel therefore makes every ROW SUM of every tile exact: the loader warps
+// publish the per-k column sums of the raw B tile (folded into their lo-conversion pass), the
+// A-converter thread of row m forms sum_k A[m,k] * colsum[k] from the row it holds in registers
+// (= the exact sum over the tile's columns of row m; round-to-nearest FP32 FMAs per k-block, float64
+// across k-blocks), the epilogue sums the row as the tensor core produced it and rescales the row
+// by the ratio before storing.  Data independent, no model of the hardware's rounding.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -53,7 +54,7 @@ namespace t32 {
 constexpr int BM = 128, BN = 128, BKF = 32;  // BKF floats = 128 bytes = one swizzle row
 constexpr int kStages = 4;
 constexpr int kRoleThreads = 128;
-constexpr int kThreadsT = 4 * kRoleThreads;       // A converters, epilogue, loaders, MMA warp + 3 sampler warps
+constexpr int kThreadsT = 3 * kRoleThreads + 3 * 32;  // A converters, epilogue, loaders, MMA warp, TMA issuers (A, B)
 constexpr int SUB_BYTES = BN * BKF * 4;           // 16 KB: B_hi or B_lo of one stage
 constexpr int STAGE_BYTES = 2 * SUB_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
@@ -69,11 +70,13 @@ static_assert(kNumBars <= 40, "barrier block is 40 words");
 constexpr int A_OFF = kStages * STAGE_BYTES;  // raw A stages follow the B stages
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)kStages * (STAGE_BYTES + SUB_BYTES) +
                               5 * 128 * sizeof(int64_t) + 2 * 128 * sizeof(double) + 40 * sizeof(uint64_t) + 64 +
-                              72 * sizeof(double) + kStages * 4 * 32 * sizeof(float);
+                              72 * sizeof(double) + (kStages + 1) * 4 * 32 * sizeof(float);
 
 enum : int32_t { kKFast = 0, kMNFast = 1, kAnyLayout = 2 };  // B staging layouts
 enum : int32_t { kFlagCVec = 1, kFlagTmaB = 2, kFlagTmaA = 32, // launch flags
                  kFlagDbgNoSample = 4, kFlagDbgNoLo = 8,       // timing experiments only (CTN_T32_DEBUG): wrong results
+                 kFlagDbgNoLoadA = 64, kFlagDbgNoLoadB = 128,  //   "  (TMA operands only: the stage is declared full unloaded)
+                 kFlagDbgNoStTmem = 1024, kFlagDbgShflDot = 2048,  //   "  (see the MMA issuer / A converters)
                  kFlagTrace = 16 };                            // CTA 0 records a time line of its pipeline events
 
 // time line of CTA 0 (CTN_T32_DEBUG=16): SM clock of event `ev` at k-block / tile ordinal `it`, one
@@ -95,6 +98,28 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one lane of the (converged) warp; the compiler knows the guarded region is single-threaded
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// (test_wait never suspends the thread; try_wait may, for a hardware-defined time)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -291,6 +316,72 @@ __device__ __forceinline__ void make_lo_linear(const unsigned char* raw_tile, un
         make_float4(residual_tf32(x[i].x), residual_tf32(x[i].y), residual_tf32(x[i].z), residual_tf32(x[i].w));
 }
 
+// TMA-filled B tile: lo conversion AND the per-k column sums of the raw tile in one pass (the values are in
+// registers anyway).  Which (column, k) a thread's chunks hold follows from the tile layout:
+//  K-major SWIZZLE_128B (row n = 128 bytes, 16-byte chunk c of row n at position c ^ (n & 7)): warp w owns the
+//    two chunks 2w, 2w+1 (k = 8w .. 8w+7) of ALL 128 rows -- lane l takes rows l, l+32, l+64, l+96 -- so that the
+//    warp's butterfly (4 + 2 + 1 halving exchanges, then lane ^ 2, lane ^ 1) ends with COMPLETE sums: part[k];
+//  MN-major box layout [32-column block][k][32 columns]: chunk i = four columns of k = 16 (i&1) + (t>>3):
+//    per-thread sums for its two k, then over the 8 lanes t&7 -> complete sums: part[k].
+template <int LAYOUT>
+__device__ __forceinline__ void make_lo_linear_sums(const unsigned char* raw_tile, unsigned char* lo_tile, int t,
+                                                    float* part /* [32] of this stage */, bool do_lo) {
+  const int lane = t & 31, w = t >> 5;
+  float4 x[8];
+  int off[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    off[i] = (LAYOUT == kMNFast) ? t * 16 + i * 2048
+                                 : (lane + 32 * (i & 3)) * 128 + (((2 * w + (i >> 2)) ^ (lane & 7)) << 4);
+    x[i] = *reinterpret_cast<const float4*>(raw_tile + off[i]);
+  }
+  if (do_lo) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(lo_tile + off[i]) =
+          make_float4(residual_tf32(x[i].x), residual_tf32(x[i].y), residual_tf32(x[i].z), residual_tf32(x[i].w));
+  }
+  if (LAYOUT == kMNFast) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      s0 += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+      s1 += (x[i + 1].x + x[i + 1].y) + (x[i + 1].z + x[i + 1].w);
+    }
+#pragma unroll
+    for (int m = 1; m <= 4; m <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+    }
+    if ((lane & 7) == 0) {
+      part[t >> 3] = s0;
+      part[16 + (t >> 3)] = s1;
+    }
+  } else {
+    float sv[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      sv[4 * h] = (x[4 * h].x + x[4 * h + 1].x) + (x[4 * h + 2].x + x[4 * h + 3].x);
+      sv[4 * h + 1] = (x[4 * h].y + x[4 * h + 1].y) + (x[4 * h + 2].y + x[4 * h + 3].y);
+      sv[4 * h + 2] = (x[4 * h].z + x[4 * h + 1].z) + (x[4 * h + 2].z + x[4 * h + 3].z);
+      sv[4 * h + 3] = (x[4 * h].w + x[4 * h + 1].w) + (x[4 * h + 2].w + x[4 * h + 3].w);
+    }
+#pragma unroll
+    for (int hh = 4; hh >= 1; hh >>= 1) {  // exchange with lane ^ 16, ^ 8, ^ 4: keep the half this lane's bit selects
+      const bool up = (lane & (4 * hh)) != 0;
+#pragma unroll
+      for (int j = 0; j < hh; ++j) {
+        const float send = up ? sv[j] : sv[j + hh];
+        const float keep = up ? sv[j + hh] : sv[j];
+        sv[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4 * hh);
+      }
+    }
+    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 2);
+    sv[0] += __shfl_xor_sync(0xffffffffu, sv[0], 1);
+    if ((lane & 3) == 0) part[8 * w + (lane >> 2)] = sv[0];  // k = 8w + 4 bit4 + 2 bit3 + bit2
+  }
+}
+
 // Output tiles in bands of 8 row tiles: the CTAs that run at the same time share few distinct
 // A row blocks and B column blocks, so both stay in L2 (126 MB) at any problem size.
 struct TileCoord {
@@ -372,6 +463,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 4);
   double* red = reinterpret_cast<double*>(tmem_slot + 16);
   float* bsum = reinterpret_cast<float*>(red + 72);  // [kStages][4 warps][32 k]: column sums of the raw B tile
+  float* bscr = bsum + kStages * 4 * 32;             // [4 A-converter warps][32 k]: the four partial sums added up
   __shared__ bool last_block;
 
   const float* A = (const float*)d.ptrs[s.in_slot[0]];
@@ -398,16 +490,17 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     for (int st = 0; st < kStages; ++st) {
       mbar_init(bar(kFullA + st), 4);    // one elected lane per A-producer warp
       mbar_init(bar(kFullB + st), 4);    // one elected lane per B-producer warp
-      mbar_init(bar(kEmpty + st), 8);    // tcgen05.commit + the three sampling warps + the four column-sum warps
+      mbar_init(bar(kEmpty + st), 5);    // tcgen05.commit + the four A-converter warps (row dots done)
       mbar_init(bar(kTmaFull + st), 1);  // TMA: one arrive.expect_tx + the transaction bytes
       mbar_init(bar(kARaw + st), TMAA ? 1 : kRoleThreads);  // TMA transaction / cp.async completion of every loader thread
-      mbar_init(bar(kARawFree + st), 7);         // one elected lane per A-converter warp and per sampler warp
-      mbar_init(bar(kBsum + st), 4);             // column sums of the B tile published by the A-converter warps
+      mbar_init(bar(kARawFree + st), 4);         // one elected lane per A-converter warp
+      mbar_init(bar(kBsum + st), 4);             // column sums of the B tile: the four loader warps (TMA path,
+                                                 // folded into the lo conversion) or the four A-converter warps
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kAccFull + b), 1);
       mbar_init(bar(kAccEmpty + b), 4);
-      mbar_init(bar(kSmpFull + b), 3);
+      mbar_init(bar(kSmpFull + b), 4);
       mbar_init(bar(kSmpEmpty + b), 4);
     }
     *abort_flag = 0;
@@ -429,14 +522,114 @@ __global__ void __launch_bounds__(kThreadsT, 1)
 
   if (warp < 4) {
     // =========================== A converters ===========================
-    // raw A tile (staged by the loader warps) -> registers -> TMEM (hi, lo)
+    // raw A tile (staged by TMA / the loader warps) -> registers -> TMEM (hi, lo); and, from the same registers, the
+    // EXACT row sum of the tile: sum_n X[r, n] = sum_k A[r, k] * (sum_n B[k, n]).
+    // The row dot of k-block `it` is taken one k-block LATE, together with the conversion of k-block it+1: it needs
+    // the B tile's column sums, and waiting for them at once would put the B conversion of the same stage on the A
+    // path.  With TMA operands all the waits come first and the two jobs share one basic block, so that their
+    // latencies overlap (these four warps set the pace of the whole pipeline once the MMAs are issued properly).
     const int r = tid;
-    uint32_t it = 0;
-    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x) {
+    uint32_t it = 0, tile_iter = 0;
+    float pv[32];  // the row of the pending k-block
+    bool pend = false, p_last = false;
+    uint32_t p_st = 0, p_ph = 0, p_buf = 0, p_ti = 0;
+    // the k-blocks are added up as an unevaluated sum of two floats (Knuth's two-sum: ~48 bits): FP64 instructions
+    // in this loop cost the converters ~900 cycles per k-block (time line), the float pair costs six FP32 adds
+    float row_hi = 0.f, row_lo = 0.f;
+    auto add_block = [&](float x) {
+      const float t = row_hi + x, bb = t - row_hi;
+      row_lo += (row_hi - (t - bb)) + (x - bb);
+      row_hi = t;
+    };
+    auto publish_if_last = [&]() {
+      if (p_last) {  // that was the tile's last k-block: hand the exact row sums to the epilogue
+        MBAR_WAIT(kSmpEmpty + p_buf, ((p_ti >> 1) & 1u) ^ 1u);
+        sample[p_buf * 128 + r] = (double)row_hi + (double)row_lo;
+        row_hi = row_lo = 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kSmpFull + p_buf));
+      }
+    };
+    // complete column sums (TMA path: the loader warps leave them at [k]): broadcast 16-byte loads
+    auto dot_complete = [&]() {
+      const float* bp = bsum + p_st * 4 * 32;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * c);
+        p0 = fmaf(pv[4 * c], b4.x, p0);
+        p1 = fmaf(pv[4 * c + 1], b4.y, p1);
+        p2 = fmaf(pv[4 * c + 2], b4.z, p2);
+        p3 = fmaf(pv[4 * c + 3], b4.w, p3);
+      }
+      add_block((p0 + p1) + (p2 + p3));
+    };
+    // cp.async path: the column sums are formed here (four partial sums per k, one per converter warp)
+    auto finish_pending_cpasync = [&]() {
+      // column sums of the raw B tile, per k: thread r takes column r's 32 k-values; a halving butterfly leaves
+      // lane l with the warp's sum for k = l
+      MBAR_WAIT(kFullB + p_st, p_ph);
+      const unsigned char* bt = tiles + p_st * STAGE_BYTES;
+      float bv[32];
+      if (LB == kMNFast) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bv[j] = *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(r, j));
+      } else {
+        const int base = (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(bt + base + ((c ^ (r & 7)) << 4));
+          bv[4 * c] = x.x; bv[4 * c + 1] = x.y; bv[4 * c + 2] = x.z; bv[4 * c + 3] = x.w;
+        }
+      }
+#pragma unroll
+      for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int j = 0; j < h; ++j) {
+          const float send = up ? bv[j] : bv[j + h];
+          const float keep = up ? bv[j + h] : bv[j];
+          bv[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+      }
+      bsum[(p_st * 4 + warp) * 32 + lane] = bv[0];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBsum + p_st));
+      MBAR_WAIT(kBsum + p_st, p_ph);
+      if (!(launch_flags & kFlagDbgNoSample)) {
+        // lane l adds up the four partial sums of k = l; the warp's scratch row then serves every lane
+        const float* bp = bsum + p_st * 4 * 32;
+        float* sc = bscr + warp * 32;
+        sc[lane] = (bp[lane] + bp[32 + lane]) + (bp[64 + lane] + bp[96 + lane]);
+        __syncwarp();
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sc + 4 * c);
+          p0 = fmaf(pv[4 * c], b4.x, p0);
+          p1 = fmaf(pv[4 * c + 1], b4.y, p1);
+          p2 = fmaf(pv[4 * c + 2], b4.z, p2);
+          p3 = fmaf(pv[4 * c + 3], b4.w, p3);
+        }
+        add_block((p0 + p1) + (p2 + p3));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kEmpty + p_st));  // done with this stage's B tile and column sums
+      publish_if_last();
+    };
+    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
+      const uint32_t buf = tile_iter & 1u;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
-        MBAR_WAIT(kARaw + st, ph);  // every loader thread's copies of this k-block have landed
+        MBAR_WAIT(kARaw + st, ph);  // the raw tile of this k-block has landed ...
         if (warp == 0) trace(launch_flags, 1, it);
+        // ... and the MMAs that read this TMEM stage have completed (with TMA for A the issuer has waited for that
+        // before loading the tile)
+        if (!TMAA) MBAR_WAIT(kEmpty + st, ph ^ 1u);
+        const bool dot_now = TMAB && pend;
+        if (dot_now) MBAR_WAIT(kBsum + p_st, p_ph);
+        if (warp == 0) trace(launch_flags, 2, it);
+        tc_fence_after();
         float v[32];
         {
           const unsigned char* at = atiles + st * SUB_BYTES;
@@ -456,20 +649,16 @@ __global__ void __launch_bounds__(kThreadsT, 1)
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kARawFree + st));  // this warp has read the stage: it may be refilled
-        MBAR_WAIT(kEmpty + st, ph ^ 1u);                   // the MMAs that read this TMEM stage have completed
-        if (warp == 0) trace(launch_flags, 2, it);
-        tc_fence_after();
+        if (dot_now && !(launch_flags & kFlagDbgNoSample)) dot_complete();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + kAStageCol0 + st * 64u;
-        {
+        if (!(launch_flags & kFlagDbgNoStTmem)) {
           uint32_t hi[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) hi[j] = __float_as_uint(v[j]);
           tc_st32(taddr, hi);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {  // eight columns at a time keeps the register peak low
+        for (int c = 0; c < 4 && !(launch_flags & kFlagDbgNoStTmem); ++c) {  // eight columns at a time keeps the register peak low
           uint32_t lo[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) lo[j] = __float_as_uint(residual_tf32(v[8 * c + j]));
@@ -478,46 +667,28 @@ __global__ void __launch_bounds__(kThreadsT, 1)
         tc_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kFullA + st));
-        if (warp == 0) trace(launch_flags, 3, it);
-        // ---- column sums of the raw B tile, per k (for the exact row sums of the samplers): thread r takes
-        // column r's 32 k-values; a halving butterfly leaves lane l with the warp's sum for k = bitrev5(l) ----
-        if (TMAB) MBAR_WAIT(kTmaFull + st, ph);
-        else MBAR_WAIT(kFullB + st, ph);
-        {
-          const unsigned char* bt = tiles + st * STAGE_BYTES;
-          float bv[32];
-          if (LB == kMNFast) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) bv[j] = *reinterpret_cast<const float*>(bt + b_elem_offset<LB, TMAB>(r, j));
-          } else {
-            const int base = (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 x = *reinterpret_cast<const float4*>(bt + base + ((c ^ (r & 7)) << 4));
-              bv[4 * c] = x.x; bv[4 * c + 1] = x.y; bv[4 * c + 2] = x.z; bv[4 * c + 3] = x.w;
-            }
-          }
-          // step with half-width h: lanes whose bit h is clear keep the lower h entries, the others the upper h
-#pragma unroll
-          for (int h = 16; h >= 1; h >>= 1) {
-            const bool up = (lane & h) != 0;
-#pragma unroll
-            for (int j = 0; j < h; ++j) {
-              const float send = up ? bv[j] : bv[j + h];
-              const float keep = up ? bv[j + h] : bv[j];
-              bv[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-            }
-          }
-          // lane l now holds k = sum over set bits: bit 4 of l -> +16, bit 3 -> +8, ... (entry index built msb first)
-          const int kidx = ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
-          bsum[(st * 4 + warp) * 32 + kidx] = bv[0];
-        }
-        __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar(kBsum + st));
-          mbar_arrive(bar(kEmpty + st));  // this warp is done with the B stage
+          mbar_arrive(bar(kFullA + st));
+          mbar_arrive(bar(kARawFree + st));  // this warp has read the raw stage: it may be refilled
+          if (dot_now) mbar_arrive(bar(kEmpty + p_st));  // done with the pending stage's column sums
         }
+        if (warp == 0) trace(launch_flags, 3, it);
+        if (dot_now) publish_if_last();
+        if (!TMAB && pend) finish_pending_cpasync();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = v[j];
+        pend = true; p_st = st; p_ph = ph; p_buf = buf; p_ti = tile_iter; p_last = (kb == nk - 1);
+      }
+    }
+    if (pend) {
+      if (TMAB) {
+        MBAR_WAIT(kBsum + p_st, p_ph);
+        if (!(launch_flags & kFlagDbgNoSample)) dot_complete();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kEmpty + p_st));
+        publish_if_last();
+      } else {
+        finish_pending_cpasync();
       }
     }
   } else if (warp < 8) {
@@ -738,14 +909,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       const bool k_in = k0 + BKF <= K && n_k == 1;
       // ---- A: raw tile, 16-byte cp.async; completion is counted on the stage's mbarrier ----
       if (TMAA) {
-        // ---- A: ONE TMA tensor box per k-block (K-fast: (32 k, 128 rows) SWIZZLE_128B; M-fast: (128 rows, 32 k)) ----
-        if (tb == 0) {
-          MBAR_WAIT(kARawFree + st, ph ^ 1u);  // the four converter warps have read the previous contents
-          mbar_expect_tx(bar(kARaw + st), (uint32_t)SUB_BYTES);
-          const uint32_t dst = smem_u32(atiles + st * SUB_BYTES);
-          if (LA == kMNFast) tma_load_4d(dst, &tmap_a, bar(kARaw + st), tci.tm * BM, kbi * BKF, tci.b, 0);
-          else tma_load_4d(dst, &tmap_a, bar(kARaw + st), kbi * BKF, tci.tm * BM, tci.b, 0);
-        }
+        // (warp 13 issues the TMA boxes of A)
       } else {
       MBAR_WAIT(kARawFree + st, ph ^ 1u);  // the four converter warps have read the previous contents
       if (warp == 8) trace(launch_flags, 21, it_i);
@@ -776,16 +940,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       if (warp == 8) trace(launch_flags, 23, it_i);
       // ---- B: one TMA tensor box issued by an elected thread, or cp.async chunks ----
       if (TMAB) {
-        if (tb == 0) {
-          MBAR_WAIT(kEmpty + st, ph ^ 1u);  // tensor core and samplers have finished with this stage
-          trace(launch_flags, 24, it_i);
-          mbar_expect_tx(bar(kTmaFull + st), (uint32_t)SUB_BYTES);
-          const uint32_t dst = smem_u32(tiles + st * STAGE_BYTES);
-          if (LB == kMNFast)  // dims: (32 n-inner, k, n-outer [32-column blocks], r or batch)
-            tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), 0, kbi * BKF, tci.tn * (npt >> 5), FUSED ? 0 : tci.b);
-          else                // dims: (k, n, batch, 1)
-            tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), kbi * BKF, tci.tn * BN, tci.b, 0);
-        }
+        // (warp 14 issues the TMA boxes of B)
       } else {
         MBAR_WAIT(kEmpty + st, ph ^ 1u);
         const uint32_t stage = smem_u32(tiles + st * STAGE_BYTES);
@@ -808,7 +963,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
           }
         }
       }
-      if (warp == 8) trace(launch_flags, 4, it_i);
+      if (warp == 8 && !TMAB) trace(launch_flags, 4, it_i);
       ++it_i;
       if (++kbi == nk) {
         kbi = 0;
@@ -838,7 +993,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       if (TMAB) {
         MBAR_WAIT(kTmaFull + st, ph);
         if (warp == 8) trace(launch_flags, 5, it);
-        if (!(launch_flags & kFlagDbgNoLo)) make_lo_linear(stage, stage + SUB_BYTES, tb);
+        make_lo_linear_sums<LB>(stage, stage + SUB_BYTES, tb, bsum + st * 4 * 32, !(launch_flags & kFlagDbgNoLo));
       } else {
         cp_async_wait<kStages - 2>();  // this thread's chunks of k-block `it` have landed
         if (warp == 8) trace(launch_flags, 5, it);
@@ -846,7 +1001,10 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kFullB + st));
+      if (lane == 0) {
+        mbar_arrive(bar(kFullB + st));
+        if (TMAB) mbar_arrive(bar(kBsum + st));  // (the column sums were written before the __syncwarp)
+      }
       if (warp == 8) trace(launch_flags, 6, it);
       issue_next();
       cp_async_commit();
@@ -862,121 +1020,102 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     const uint32_t b_lbo = (LB == kMNFast) ? (TMAB ? 4096u : 512u) : 16u;
     const uint32_t b_sbo = (LB == kMNFast) ? (TMAB ? 512u : 2048u) : 1024u;
     const uint32_t b_ty = (LB == kMNFast) ? 1u : 2u;
-    if (lane == 0) {  // a single thread issues everything: no warp-level synchronisation in the loop
+    // The WHOLE warp runs the loop (warp-uniform control flow, uniform registers for the descriptors) and one
+    // lane chosen by elect.sync issues: issuing from a divergent `if (lane == 0)` region makes the compiler wrap
+    // every tcgen05 instruction in a serialising loop over the possibly-active lanes, which cost ~120 cycles per
+    // MMA -- more than the MMA itself (measured with the time line: 360 cycles per k-step whether it held one
+    // MMA or three).
+    const uint64_t desc0 = make_desc(0u, b_lbo, b_sbo, b_ty);  // + (shared address >> 4): stays inside the 14-bit field
+    {
       uint32_t it = 0, tile_iter = 0;
-      bool ready = false;  // operands of k-block `it` already awaited (done while the previous MMAs ran)
       for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
         const uint32_t buf = tile_iter & 1u;
         MBAR_WAIT(kAccEmpty + buf, ((tile_iter >> 1) & 1u) ^ 1u);  // the epilogue has drained this buffer
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + kAccCol0 + buf * 128u;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
-          if (!ready) {
-            MBAR_WAIT(kFullA + st, ph);
-            trace(launch_flags, 7, it);
-            MBAR_WAIT(kFullB + st, ph);
-            trace(launch_flags, 8, it);
-          }
-          ready = false;
+          MBAR_WAIT(kFullA + st, ph);
+          trace(launch_flags, 7, it);
+          MBAR_WAIT(kFullB + st, ph);
+          trace(launch_flags, 8, it);
           tc_fence_after();
           const uint32_t a_col = tmem_base + kAStageCol0 + st * 64u;
-          const uint32_t sb = smem_u32(tiles + st * STAGE_BYTES);
-          const uint32_t b_hi = sb, b_lo = sb + SUB_BYTES;
+          const uint64_t d_hi = desc0 + (uint64_t)(smem_u32(tiles + st * STAGE_BYTES) >> 4), d_lo = d_hi + (uint64_t)(SUB_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BKF / 8; ++ks) {
-            // one UMMA_K = 8 floats: 32 bytes along K (K-major) or two k-atoms (MN-major)
-            const uint32_t bo = (LB == kMNFast) ? (uint32_t)ks * 2u * b_sbo : (uint32_t)ks * 32u;
-            const uint64_t dbh = make_desc(b_hi + bo, b_lbo, b_sbo, b_ty), dbl = make_desc(b_lo + bo, b_lbo, b_sbo, b_ty);
-            const uint32_t a_hi = a_col + (uint32_t)ks * 8u, a_lo = a_col + 32u + (uint32_t)ks * 8u;
-            if (ks == BKF / 8 - 1 && it + 1 < total_it) {
-              // the tensor core is busy with this k-block's first MMAs: look whether the NEXT k-block's operands
-              // are there already, so that its MMAs can be queued back to back (same tile only: a new tile
-              // also needs its accumulator buffer)
-              if (kb + 1 < nk) {
-                // (a non-blocking test: stalling here would delay this k-block's commit and with it the
-                // refill of its stage)
-                const uint32_t st2 = (it + 1) & (kStages - 1), ph2 = ((it + 1) / kStages) & 1u;
-                ready = mbar_try(bar(kFullA + st2), ph2) && mbar_try(bar(kFullB + st2), ph2);
-              }
+            for (int ks = 0; ks < BKF / 8; ++ks) {
+              // one UMMA_K = 8 floats: 32 bytes along K (K-major) or two k-atoms (MN-major)
+              const uint32_t bo = (LB == kMNFast) ? (uint32_t)ks * 2u * b_sbo : (uint32_t)ks * 32u;
+              const uint64_t dbh = d_hi + (uint64_t)(bo >> 4), dbl = d_lo + (uint64_t)(bo >> 4);
+              const uint32_t a_hi = a_col + (uint32_t)ks * 8u, a_lo = a_col + 32u + (uint32_t)ks * 8u;
+              tc_mma_ts(d_tmem, a_lo, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              tc_mma_ts(d_tmem, a_hi, dbl, idesc, 1u);
+              tc_mma_ts(d_tmem, a_hi, dbh, idesc, 1u);
             }
-            tc_mma_ts(d_tmem, a_lo, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            tc_mma_ts(d_tmem, a_hi, dbl, idesc, 1u);
-            tc_mma_ts(d_tmem, a_hi, dbh, idesc, 1u);
+            tc_commit(bar(kEmpty + st));  // stage free once these MMAs have read it
+            if (kb == nk - 1) tc_commit(bar(kAccFull + buf));
           }
-          tc_commit(bar(kEmpty + st));  // stage free once these MMAs have read it
-          if (kb == nk - 1) tc_commit(bar(kAccFull + buf));
+          __syncwarp();
           trace(launch_flags, 9, it);
         }
       }
     }
-    __syncwarp();
-  } else {
-    // =========================== samplers (warps 13-15) ===========================
-    // EXACT row sums of the tile, sum_n X[m, n] = sum_k A[m, k] * (sum_n B[k, n]), round-to-nearest FMAs over the raw
-    // A rows (shared memory) and the B column sums published by the A-converter warps.  96 threads cover the
-    // 128 rows: thread i takes row i, the first 32 also row 96 + i.
-    const int i0 = (warp - 13) * 32 + lane;
-    const bool two = warp == 13;  // (uniform per warp)
-    uint32_t it = 0, tile_iter = 0;
-    for (uint32_t w = blockIdx.x; w < total; w += gridDim.x, ++tile_iter) {
-      const uint32_t buf = tile_iter & 1u;
-      double acc_a = 0.0, acc_b = 0.0;
-      for (int kb = 0; kb < nk; ++kb, ++it) {
-        const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
-        MBAR_WAIT(kARaw + st, ph);
-        float va[32], vb[32];
-        {
-          const unsigned char* at = atiles + st * SUB_BYTES;
-          auto read_row = [&](int r, float (&v)[32]) {
-            if (LA == kMNFast && TMAA) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + j * 512 + r * 4);
-            } else if (LA == kMNFast) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = *reinterpret_cast<const float*>(at + b_elem_offset<kMNFast, false>(r, j));
+  } else if (warp == 13) {
+    // =========================== TMA issuer, A (warp 13) ===========================
+    // ONE tensor box per k-block (K-fast: (32 k, 128 rows) SWIZZLE_128B; M-fast: (128 rows, 32 k)).  A thread of
+    // its own: it blocks on "stage free" without holding up anybody's conversions, so all four stages stay in flight.
+    // (warp-uniform loop, one elected lane issues: see the MMA issuer)
+    if (TMAA) {
+      uint32_t it = 0;
+      for (uint32_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const TileCoord tc = decode_tile(w, tilesM, tilesN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
+          MBAR_WAIT(kARawFree + st, ph ^ 1u);  // the four converter warps have read the previous contents ...
+          MBAR_WAIT(kEmpty + st, ph ^ 1u);     // ... and the MMAs that read the TMEM stage this tile is converted
+                                               // into have completed (the converters rely on that)
+          trace(launch_flags, 21, it);
+          if (elect_one()) {
+            if (launch_flags & kFlagDbgNoLoadA) {
+              mbar_arrive(bar(kARaw + st));
             } else {
-              const int base = (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 x = *reinterpret_cast<const float4*>(at + base + ((c ^ (r & 7)) << 4));
-                v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
-              }
-            }
-          };
-          read_row(i0, va);
-          if (two) read_row(96 + i0, vb);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kARawFree + st));
-        MBAR_WAIT(kBsum + st, ph);
-        const float* bp = bsum + st * 4 * 32;
-        const float bs = (bp[lane] + bp[32 + lane]) + (bp[64 + lane] + bp[96 + lane]);  // column sum for k = lane
-        if (!(launch_flags & kFlagDbgNoSample)) {
-          // 32 terms per k-block in round-to-nearest FP32 FMAs (four independent chains; ~1e-7 relative, zero
-          // mean), the k-blocks added in float64: a dependent chain of 32 float64 FMAs per k-block made these
-          // warps the slowest stage of the pipeline
-          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float b0 = __shfl_sync(0xffffffffu, bs, j), b1 = __shfl_sync(0xffffffffu, bs, j + 1);
-            const float b2 = __shfl_sync(0xffffffffu, bs, j + 2), b3 = __shfl_sync(0xffffffffu, bs, j + 3);
-            p0 = fmaf(va[j], b0, p0); p1 = fmaf(va[j + 1], b1, p1); p2 = fmaf(va[j + 2], b2, p2); p3 = fmaf(va[j + 3], b3, p3);
-            if (two) {
-              q0 = fmaf(vb[j], b0, q0); q1 = fmaf(vb[j + 1], b1, q1); q2 = fmaf(vb[j + 2], b2, q2); q3 = fmaf(vb[j + 3], b3, q3);
+              mbar_expect_tx(bar(kARaw + st), (uint32_t)SUB_BYTES);
+              const uint32_t dst = smem_u32(atiles + st * SUB_BYTES);
+              if (LA == kMNFast) tma_load_4d(dst, &tmap_a, bar(kARaw + st), tc.tm * BM, kb * BKF, tc.b, 0);
+              else tma_load_4d(dst, &tmap_a, bar(kARaw + st), kb * BKF, tc.tm * BM, tc.b, 0);
             }
           }
-          acc_a += (double)((p0 + p1) + (p2 + p3));
-          if (two) acc_b += (double)((q0 + q1) + (q2 + q3));
+          __syncwarp();
+          trace(launch_flags, 23, it);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kEmpty + st));  // done with this stage's column sums
       }
-      MBAR_WAIT(kSmpEmpty + buf, ((tile_iter >> 1) & 1u) ^ 1u);
-      sample[buf * 128 + i0] = acc_a;
-      if (two) sample[buf * 128 + 96 + i0] = acc_b;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kSmpFull + buf));
+    }
+  } else if (warp == 14) {
+    // =========================== TMA issuer, B (warp 14) ===========================
+    if (TMAB) {
+      uint32_t it = 0;
+      for (uint32_t w = blockIdx.x; w < total; w += gridDim.x) {
+        const TileCoord tc = decode_tile(w, tilesM, tilesN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const uint32_t st = it & (kStages - 1), ph = (it / kStages) & 1u;
+          MBAR_WAIT(kEmpty + st, ph ^ 1u);  // tensor core and row dots have finished with this stage
+          trace(launch_flags, 24, it);
+          if (elect_one()) {
+            if (launch_flags & kFlagDbgNoLoadB) {
+              mbar_arrive(bar(kTmaFull + st));
+            } else {
+              mbar_expect_tx(bar(kTmaFull + st), (uint32_t)SUB_BYTES);
+              const uint32_t dst = smem_u32(tiles + st * STAGE_BYTES);
+              if (LB == kMNFast)  // dims: (32 n-inner, k, n-outer [32-column blocks], r or batch)
+                tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), 0, kb * BKF, tc.tn * (npt >> 5), FUSED ? 0 : tc.b);
+              else                // dims: (k, n, batch, 1)
+                tma_load_4d(dst, &tmap_b, bar(kTmaFull + st), kb * BKF, tc.tn * BN, tc.b, 0);
+            }
+          }
+          __syncwarp();
+          trace(launch_flags, 4, it);
+        }
+      }
     }
   }
 #undef MBAR_WAIT
@@ -1297,7 +1436,9 @@ cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, 
     static const bool no_tma_a = getenv("CTN_TF32_NO_TMA_A") != nullptr;
     if (!no_tma_a && a_aligned && tma_shape_a(g, la, shape) && get_tensor_map(shape, a_ptr, tmap_a)) flags |= kFlagTmaA;
   }
-  static const int dbg = getenv("CTN_T32_DEBUG") ? atoi(getenv("CTN_T32_DEBUG")) & (kFlagDbgNoSample | kFlagDbgNoLo | kFlagTrace) : 0;
+  static const int dbg = getenv("CTN_T32_DEBUG") ? atoi(getenv("CTN_T32_DEBUG")) &
+                                                       (kFlagDbgNoSample | kFlagDbgNoLo | kFlagTrace | kFlagDbgNoLoadA | kFlagDbgNoLoadB | kFlagDbgNoStTmem | kFlagDbgShflDot)
+                                                 : 0;
   flags |= dbg;
   switch (lb) {
     case kKFast: return launch_modes<kKFast>(c, l, g, la, flags, tmap, tmap_a);

@@ -2,7 +2,7 @@
 happened on SM 0 (cycles relative to the kernel's start).  python tools/t32_trace.py <t32_check case>"""
 import ctypes, os, sys
 import numpy as np
-os.environ["CTN_T32_DEBUG"] = "16"
+os.environ["CTN_T32_DEBUG"] = str(16 | int(os.environ.get("CTN_T32_EXTRA", "0")))  # extra timing-experiment flags
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from contractn_b200 import engine, planner
@@ -44,6 +44,11 @@ for c in (20, 17, 10, 13, 14, 15, 16, 12, 30, 27, 28, 31):
     for it in range(8):
         if t[c, it] > 0:
             print(f"   {names[c]:>18} [{it}] at {int(t[c, it] - t0)}")
+if t[11, 1] > 0:  # inside the A converters: landed -> stage free -> FullA -> [pending row dot: enter, sums there, dot done, left]
+    print("A converter, k-blocks 8..15: landed->free  ->FullA  ->enter dot  ->sums there  ->dot done  ->left  ->next landed")
+    for it in range(8, min(n_it - 1, 16)):
+        print(f"{it:4d}  {int(t[2, it] - t[1, it]):6d} {int(t[3, it] - t[2, it]):6d} {int(t[11, it] - t[3, it]):6d} "
+              f"{int(t[18, it] - t[11, it]):6d} {int(t[19, it] - t[18, it]):6d} {int(t[25, it] - t[19, it]):6d} {int(t[1, it + 1] - t[25, it]):6d}")
 d = np.diff(t[9, :n_it])
 if len(d) > 4:
     print("cycles between consecutive 'mma issued': median", int(np.median(d)), "mean", int(d.mean()))
