@@ -34,9 +34,10 @@
 // sweep by 1e-4.  The kernel therefore makes every ROW SUM of every tile exact: the loader warps
 // publish the per-k column sums of the raw B tile (folded into their lo-conversion pass), the
 // A-converter thread of row m forms sum_k A[m,k] * colsum[k] from the row it holds in registers
-// (= the exact sum over the tile's columns of row m; round-to-nearest FP32 FMAs per k-block, float64
-// across k-blocks), the epilogue sums the row as the tensor core produced it and rescales the row
-// by the ratio before storing.  Data independent, no model of the hardware's rounding.
+// (= the exact sum over the tile's columns of row m; round-to-nearest FP32 FMAs per k-block, the
+// k-blocks added up as a pair of floats), the epilogue sums the row as the tensor core produced it
+// and rescales the row by the ratio before storing.  Data independent, no model of the hardware's
+// rounding.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -76,7 +77,7 @@ enum : int32_t { kKFast = 0, kMNFast = 1, kAnyLayout = 2 };  // B staging layout
 enum : int32_t { kFlagCVec = 1, kFlagTmaB = 2, kFlagTmaA = 32, // launch flags
                  kFlagDbgNoSample = 4, kFlagDbgNoLo = 8,       // timing experiments only (CTN_T32_DEBUG): wrong results
                  kFlagDbgNoLoadA = 64, kFlagDbgNoLoadB = 128,  //   "  (TMA operands only: the stage is declared full unloaded)
-                 kFlagDbgNoStTmem = 1024, kFlagDbgShflDot = 2048,  //   "  (see the MMA issuer / A converters)
+                 kFlagDbgNoStTmem = 1024,  //   "  (see the MMA issuer / A converters)
                  kFlagTrace = 16 };                            // CTA 0 records a time line of its pipeline events
 
 // time line of CTA 0 (CTN_T32_DEBUG=16): SM clock of event `ev` at k-block / tile ordinal `it`, one
@@ -98,6 +99,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// (hi, lo) += x with Knuth's two-sum: the pair carries ~48 bits
+__device__ __forceinline__ void two_sum_add(float& hi, float& lo, float x) {
+  const float t = hi + x, bb = t - hi;
+  lo += (hi - (t - bb)) + (x - bb);
+  hi = t;
 }
 // one lane of the (converged) warp; the compiler knows the guarded region is single-threaded
 __device__ __forceinline__ bool elect_one() {
@@ -180,6 +187,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// (the TMEM stores carry no memory clobber: they read registers only, and independent shared-memory loads may be
+// scheduled past them)
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -188,13 +197,11 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
         "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]));
 }
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
 }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // stores through the global window (the output pointer comes out of a table, so the compiler would
@@ -416,26 +423,6 @@ __device__ __forceinline__ int64_t mode_offset(const GemmMode* modes, int n, int
   return o;
 }
 
-// Four block-wide sums in one pass, fixed order (deterministic).  Results valid in all threads.
-__device__ __forceinline__ void block_sum4(double (&v)[4], double* sm /* >= 4 * 17 doubles */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = warp_sum(v[i]);
-  __syncthreads();
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sm[i * 17 + warp] = v[i];
-  }
-  __syncthreads();
-  if (warp < 4) {
-    double t = lane < nw ? sm[warp * 17 + lane] : 0.0;
-    t = warp_sum(t);
-    if (lane == 0) sm[warp * 17 + 16] = t;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = sm[i * 17 + 16];
-}
 
 // several summed modes in A: per-element decomposition, deliberately NOT inlined (it is called from a
 // fully unrolled 32-element loop in 24 kernel instantiations)
@@ -457,7 +444,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   int64_t* coltab = reinterpret_cast<int64_t*>(smem + kStages * (STAGE_BYTES + SUB_BYTES));  // [2][128] B producers
   int64_t* rowtab = coltab + 256;                                                             // [2][128] A producers
   int64_t* colC = rowtab + 256;                                                               // [128]    epilogue
-  double* sample = reinterpret_cast<double*>(colC + 128);                                     // [2][128] exact entries
+  float2* sample = reinterpret_cast<float2*>(colC + 128);                                     // [2][128] exact row sums (hi, lo)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sample + 2 * 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 4);
@@ -518,7 +505,9 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 12) trace(launch_flags, 0, 0);
 
-  double local_abs = 0.0, local_abs_t = 0.0;  // sum|out| and (fused) sum|X|         (epilogue threads)
+  // sum|out| and (fused) sum|X| of the epilogue threads, each an unevaluated sum of two floats (FP64 instructions
+  // are kept out of the per-tile paths: their latency is what the single warp per scheduler cannot hide)
+  float abs_hi = 0.f, abs_lo = 0.f, abst_hi = 0.f, abst_lo = 0.f;
 
   if (warp < 4) {
     // =========================== A converters ===========================
@@ -536,15 +525,11 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     // the k-blocks are added up as an unevaluated sum of two floats (Knuth's two-sum: ~48 bits): FP64 instructions
     // in this loop cost the converters ~900 cycles per k-block (time line), the float pair costs six FP32 adds
     float row_hi = 0.f, row_lo = 0.f;
-    auto add_block = [&](float x) {
-      const float t = row_hi + x, bb = t - row_hi;
-      row_lo += (row_hi - (t - bb)) + (x - bb);
-      row_hi = t;
-    };
+    auto add_block = [&](float x) { two_sum_add(row_hi, row_lo, x); };
     auto publish_if_last = [&]() {
       if (p_last) {  // that was the tile's last k-block: hand the exact row sums to the epilogue
         MBAR_WAIT(kSmpEmpty + p_buf, ((p_ti >> 1) & 1u) ^ 1u);
-        sample[p_buf * 128 + r] = (double)row_hi + (double)row_lo;
+        sample[p_buf * 128 + r] = make_float2(row_hi, row_lo);
         row_hi = row_lo = 0.f;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kSmpFull + p_buf));
@@ -649,7 +634,6 @@ __global__ void __launch_bounds__(kThreadsT, 1)
             }
           }
         }
-        if (dot_now && !(launch_flags & kFlagDbgNoSample)) dot_complete();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + kAStageCol0 + st * 64u;
         if (!(launch_flags & kFlagDbgNoStTmem)) {
           uint32_t hi[32];
@@ -664,6 +648,8 @@ __global__ void __launch_bounds__(kThreadsT, 1)
           for (int j = 0; j < 8; ++j) lo[j] = __float_as_uint(residual_tf32(v[8 * c + j]));
           tc_st8(taddr + 32u + 8u * (uint32_t)c, lo);
         }
+        // (the pending row dot runs while the TMEM stores are in flight)
+        if (dot_now && !(launch_flags & kFlagDbgNoSample)) dot_complete();
         tc_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -737,30 +723,35 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol0 + buf * 128u;
       // ---- pass 1: this row's sum over the tile as the tensor core produced it; with the samplers' exact row
       // sum it gives the row's accumulator-truncation factor, applied to every entry of the row below ----
-      double rs = 0.0, rs_abs = 0.0;
+      float rs_hi = 0.f, rs_lo = 0.f, rs_abs = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t a[32];
         tc_ld32(tbase + (uint32_t)cc * 32u, a);
         tc_ld_wait();
-        float part = 0.f, part_abs = 0.f;
+        float pa[4] = {0.f, 0.f, 0.f, 0.f}, part_abs = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          part += __uint_as_float(a[j]);
+          pa[j & 3] += __uint_as_float(a[j]);
           part_abs += fabsf(__uint_as_float(a[j]));
         }
-        rs += (double)part;
-        rs_abs += (double)part_abs;
+        two_sum_add(rs_hi, rs_lo, (pa[0] + pa[1]) + (pa[2] + pa[3]));
+        rs_abs += part_abs;
       }
+      if (q == 0 && FUSED) trace(launch_flags, 13, tile_iter);
       MBAR_WAIT(kSmpFull + buf, (tile_iter >> 1) & 1u);
-      const double ex = sample[buf * 128 + r];
+      const float2 ex = sample[buf * 128 + r];
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kSmpEmpty + buf));
-      // the ratio is well conditioned only when the row does not cancel (same-sign data: |sum| = sum|.|); a row of
-      // mixed signs is left alone (its truncation errors are not a common factor anyway)
-      double rho = (fabs(rs) > 0.5 * rs_abs && ex != 0.0) ? ex / rs : 1.0;
-      if (!(fabs(rho - 1.0) < 1e-3)) rho = 1.0;
-      const float alpha = (float)((double)alpha0 * rho);
+      // rho - 1 = (exact - tc) / tc: the leading parts are within a factor of 1 + 1e-3 of each other, so their
+      // difference is exact (Sterbenz) and the quotient needs no more than FP32.  The ratio is well conditioned only
+      // when the row does not cancel (same-sign data: |sum| = sum|.|); a row of mixed signs is left alone (its
+      // truncation errors are not a common factor anyway)
+      float rel = 0.f;
+      if (fabsf(rs_hi) > 0.5f * rs_abs && ex.x != 0.f) rel = ((ex.x - rs_hi) + (ex.y - rs_lo)) / rs_hi;
+      if (!(fabsf(rel) < 1e-3f)) rel = 0.f;
+      const float alpha = fmaf(alpha0, rel, alpha0);
+      if (q == 0 && FUSED) trace(launch_flags, 14, tile_iter);
       float lf = 0.f, lt = 0.f;
       float* Crow = C + oc + (lin ? (int64_t)tc.tn * npt * scn : 0);
       // (rows / columns outside the problem were zero-filled on the way in, so their accumulator entries are
@@ -829,6 +820,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
               o[j] = fmaf(t, wv, o[j]);
             }
           }
+          if (q == 0 && nc == 0) trace(launch_flags, 15, tile_iter);
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -838,11 +830,18 @@ __global__ void __launch_bounds__(kThreadsT, 1)
               lf += fabsf(o[j]);
             }
           }
+          if (q == 0 && nc == 0) trace(launch_flags, 16, tile_iter);
         }
       }
-      local_abs += (double)lf;
-      local_abs_t += (double)lt;
+      two_sum_add(abs_hi, abs_lo, lf);
+      two_sum_add(abst_hi, abst_lo, lt);
       if (q == 0) trace(launch_flags, 12, tile_iter);
+    }
+    // this warp's share of sum|out| and sum|X| (the only non-zero ones of the CTA)
+    const double wa = warp_sum((double)abs_hi + (double)abs_lo), wt = warp_sum((double)abst_hi + (double)abst_lo);
+    if (lane == 0) {
+      red[2 * q] = wa;
+      red[2 * q + 1] = wt;
     }
   } else if (warp < 12) {
     // =========================== loaders (A and B) + B converters ===========================
@@ -1128,14 +1127,10 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
-  double sums[4] = {local_abs, local_abs_t, 0.0, 0.0};
-  block_sum4(sums, red);
   if (warp == 12) trace(launch_flags, 27, 0);
-  if (tid == 0) {
-    d.partials[blockIdx.x] = sums[0];
-    d.partials[kMaxPartials + blockIdx.x] = sums[1];
-    d.partials[2 * kMaxPartials + blockIdx.x] = sums[2];
-    d.partials[3 * kMaxPartials + blockIdx.x] = sums[3];
+  if (tid == 0) {  // (the four epilogue warps left their sums in `red` before the barrier above)
+    d.partials[blockIdx.x] = (red[0] + red[2]) + (red[4] + red[6]);
+    d.partials[kMaxPartials + blockIdx.x] = (red[1] + red[3]) + (red[5] + red[7]);
     __threadfence();
     const uint32_t tk = atomicAdd(&d.tickets[s.ticket], 1u);
     last_block = (tk == gridDim.x - 1);
@@ -1144,15 +1139,26 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   if (warp == 12) trace(launch_flags, 28, 0);
   if (last_block) {
     __threadfence();
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    double a0 = 0.0, a1 = 0.0;
     for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
       a0 += __ldcg(&d.partials[i]);
       a1 += __ldcg(&d.partials[kMaxPartials + i]);
-      a2 += __ldcg(&d.partials[2 * kMaxPartials + i]);
-      a3 += __ldcg(&d.partials[3 * kMaxPartials + i]);
     }
-    double tot[4] = {a0, a1, a2, a3};
-    block_sum4(tot, red);
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+      red[8 + 2 * warp] = a0;
+      red[9 + 2 * warp] = a1;
+    }
+    __syncthreads();
+    double tot[2] = {0.0, 0.0};
+    if (tid == 0) {
+      const int nw = min(kThreadsT / 32, ((int)gridDim.x + 31) / 32);  // (the other warps hold zeros)
+      for (int i = 0; i < nw; ++i) {
+        tot[0] += red[8 + 2 * i];
+        tot[1] += red[9 + 2 * i];
+      }
+    }
     const double norm = tot[0], norm_x = tot[1];
     if (tid == 0) {
       if (FUSED) {
@@ -1376,7 +1382,9 @@ static cudaError_t launch_modes(const ExecCtx& c, const Launch& l, const GemmDev
 
 // Debug aid (not part of the documented ABI): copy out and clear CTA 0's event time line
 // ([event][ordinal] SM clocks, 0 = not recorded).
+namespace t32 { static int g_trace_launch = 0; }  // gemm launches since the time line was last read
 extern "C" int ctn_debug_t32_trace(long long* host_out, int cap) {
+  t32::g_trace_launch = 0;
   const int n = std::min(cap, t32::kTraceEvents * t32::kTraceIts);
   if (cudaMemcpyFromSymbol(host_out, t32::g_trace, (size_t)n * sizeof(long long)) != cudaSuccess) return -1;
   static long long zeros[t32::kTraceEvents * t32::kTraceIts];
@@ -1437,9 +1445,13 @@ cudaError_t launch_gemm_tf32(const ExecCtx& c, const Launch& l, bool a_aligned, 
     if (!no_tma_a && a_aligned && tma_shape_a(g, la, shape) && get_tensor_map(shape, a_ptr, tmap_a)) flags |= kFlagTmaA;
   }
   static const int dbg = getenv("CTN_T32_DEBUG") ? atoi(getenv("CTN_T32_DEBUG")) &
-                                                       (kFlagDbgNoSample | kFlagDbgNoLo | kFlagTrace | kFlagDbgNoLoadA | kFlagDbgNoLoadB | kFlagDbgNoStTmem | kFlagDbgShflDot)
+                                                       (kFlagDbgNoSample | kFlagDbgNoLo | kFlagTrace | kFlagDbgNoLoadA | kFlagDbgNoLoadB | kFlagDbgNoStTmem)
                                                  : 0;
   flags |= dbg;
+  // CTN_T32_TRACE_LAUNCH=n: only the n-th launch after the time line was last read records (default: every launch
+  // does, the last one's records survive)
+  static const int trace_launch = getenv("CTN_T32_TRACE_LAUNCH") ? atoi(getenv("CTN_T32_TRACE_LAUNCH")) : -1;
+  if (trace_launch >= 0 && g_trace_launch++ != trace_launch) flags &= ~kFlagTrace;
   switch (lb) {
     case kKFast: return launch_modes<kKFast>(c, l, g, la, flags, tmap, tmap_a);
     case kMNFast: return launch_modes<kMNFast>(c, l, g, la, flags, tmap, tmap_a);

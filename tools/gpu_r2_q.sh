@@ -1,6 +1,11 @@
 #!/bin/bash
-# A-converter time line + row-dot variants
 mkdir -p gpurun_out
-for f in 0 2048 4; do echo "== extra flags $f"; CTN_T32_EXTRA=$f timeout 300 python tools/t32_trace.py 10 2>&1 | tail -11; done
-echo "== case 11/21 (MN-major B)"; timeout 300 python tools/t32_trace.py 11 2>&1 | tail -11
-for f in 0 2048; do echo "== CTN_T32_DEBUG=$f"; CTN_T32_DEBUG=$f timeout 300 python tools/t32_check.py 10 11 12 2>&1 | grep "TFLOP\|OUT OF"; done
+for v in "" 1; do
+echo "== CTN_TF32_NO_PDL=$v"
+CTN_TF32_NO_PDL=$v timeout 600 python bench.py --steps 50 --warmup 5 --configs cfg3 2>/dev/null | python -c "
+import json,sys
+r=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=1: value', r['value'], 'ms/step', r['ms_per_step'], r['clocks'])
+for c in r.get('configs', []): print(c['ms_per_contraction'], c['roofline']['frac'], c['errors'], c['ms_by_kernel_class'])"
+done
+timeout 600 python tools/t32_check.py 0 2 8 12 15 21 2>&1 | grep "OUT OF\|done,\|TFLOP\|flags [1-9]"
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_full_size.py -m gpu -x -q 2>&1 | tail -3

@@ -32,8 +32,8 @@ names = {0: "start", 1: "A raw landed", 2: "A tmem free", 3: "FullA", 4: "issued
 # (with several gemm launches in the plan the LAST launch's records survive)
 t0 = t[0, 0]
 cols = [21, 22, 23, 24, 4, 1, 2, 3, 5, 6, 7, 8, 9]
-names.update({21: "i:A free", 22: "i:A copies", 23: "i:A arrive", 24: "i:B free", 13: "epi: ld0", 14: "epi: ld1", 15: "epi: ld2",
-              16: "epi: ld3", 17: "epi: table ready", 27: "block sums done", 28: "ticket done"})
+names.update({21: "i:A free", 22: "i:A copies", 23: "i:A arrive", 24: "i:B free", 13: "epi: ld0 | pass 1 done", 14: "epi: ld1 | alpha ready", 15: "epi: ld2 | chunk 0 computed",
+              16: "epi: ld3 | chunk 0 stored", 17: "epi: table ready", 27: "block sums done", 28: "ticket done"})
 n_it = int((t[9] > 0).sum())
 print(f"k-blocks recorded: {n_it}; span start->end {t[31, 0] - t0} cycles")
 print("it    " + " ".join(f"{names[c][:12]:>12}" for c in cols))
@@ -43,7 +43,7 @@ for it in show:
 for c in (20, 17, 10, 13, 14, 15, 16, 12, 30, 27, 28, 31):
     for it in range(8):
         if t[c, it] > 0:
-            print(f"   {names[c]:>18} [{it}] at {int(t[c, it] - t0)}")
+            print(f"   {names[c]:>30} [{it}] at {int(t[c, it] - t0)}")
 if t[11, 1] > 0:  # inside the A converters: landed -> stage free -> FullA -> [pending row dot: enter, sums there, dot done, left]
     print("A converter, k-blocks 8..15: landed->free  ->FullA  ->enter dot  ->sums there  ->dot done  ->left  ->next landed")
     for it in range(8, min(n_it - 1, 16)):
