@@ -89,6 +89,16 @@ __device__ __forceinline__ void trace(int flags, int ev, unsigned it) {
     g_trace[ev * kTraceIts + it] = clock64();
 }
 
+// wall-clock marks (event row 29, nanoseconds of %globaltimer): [0] CTA 0 enters, [1] CTA 0 leaves, [2] the last CTA
+// (whoever it is: [3]) has recorded the scale -- against the launch's duration they show what CTA 0's time line misses
+__device__ __forceinline__ void trace_wall(int flags, int slot, long long extra = -1, int row = 29) {
+  if (flags & kFlagTrace) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[row * kTraceIts + slot] = extra >= 0 ? extra : t;
+  }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -437,6 +447,9 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   // (the step and its GEMM view travel in the kernel parameters: no dependent descriptor loads from
   // global memory at the head of every launch)
   extern __shared__ unsigned char smem_dyn[];
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_wall(launch_flags, 0);
+  if ((threadIdx.x >> 5) == 12) trace(launch_flags, 18, 0);  // SM clock at entry
+  if (threadIdx.x == 0) trace_wall(launch_flags, (int)blockIdx.x, -1, 19);  // every CTA: wall clock at entry (row 19) ...
   const uint32_t raw = smem_u32(smem_dyn);
   unsigned char* smem = smem_dyn + ((1024u - (raw & 1023u)) & 1023u);
   unsigned char* tiles = smem;           // B stages: [hi | lo] x kStages
@@ -473,31 +486,24 @@ __global__ void __launch_bounds__(kThreadsT, 1)
   StateHdr* hdr = d.hdr;
 #define MBAR_WAIT(idx, parity) mbar_wait(bar(idx), (parity), abort_flag, hdr, (idx))
 
-  if (tid == 0) {
-    for (int st = 0; st < kStages; ++st) {
-      mbar_init(bar(kFullA + st), 4);    // one elected lane per A-producer warp
-      mbar_init(bar(kFullB + st), 4);    // one elected lane per B-producer warp
-      mbar_init(bar(kEmpty + st), 5);    // tcgen05.commit + the four A-converter warps (row dots done)
-      mbar_init(bar(kTmaFull + st), 1);  // TMA: one arrive.expect_tx + the transaction bytes
-      mbar_init(bar(kARaw + st), TMAA ? 1 : kRoleThreads);  // TMA transaction / cp.async completion of every loader thread
-      mbar_init(bar(kARawFree + st), 4);         // one elected lane per A-converter warp
-      mbar_init(bar(kBsum + st), 4);             // column sums of the B tile: the four loader warps (TMA path,
-                                                 // folded into the lo conversion) or the four A-converter warps
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar(kAccFull + b), 1);
-      mbar_init(bar(kAccEmpty + b), 4);
-      mbar_init(bar(kSmpFull + b), 4);
-      mbar_init(bar(kSmpEmpty + b), 4);
-    }
-    *abort_flag = 0;
+  // one barrier per thread (a single thread initialising all of them cost ~1900 cycles at the head of every launch)
+  if (tid < kNumBars) {
+    uint32_t cnt = 4;  // FullA, FullB, ARawFree, Bsum, AccEmpty, SmpFull, SmpEmpty: one elected lane of each of four warps
+    if (tid >= kEmpty && tid < kTmaFull) cnt = 5;             // tcgen05.commit + the four A-converter warps (row dots done)
+    else if (tid >= kTmaFull && tid < kARaw) cnt = 1;         // TMA: one arrive.expect_tx + the transaction bytes
+    else if (tid >= kARaw && tid < kARawFree) cnt = TMAA ? 1 : kRoleThreads;  // TMA transaction / cp.async completion of every loader thread
+    else if (tid >= kAccFull && tid < kAccEmpty) cnt = 1;     // tcgen05.commit
+    mbar_init(bar(tid), cnt);
+    if (tid == 0) *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (tid == 0) trace(launch_flags, 18, 1);  // barriers initialised
   }
   if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    trace(launch_flags, 18, 2);  // TMEM allocated
   }
   tc_fence_before();
   __syncthreads();
@@ -1128,6 +1134,7 @@ __global__ void __launch_bounds__(kThreadsT, 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
   if (warp == 12) trace(launch_flags, 27, 0);
+  if (tid == 0) trace_wall(launch_flags, (int)blockIdx.x, -1, 25);  // ... and when its roles are done (row 25)
   if (tid == 0) {  // (the four epilogue warps left their sums in `red` before the barrier above)
     d.partials[blockIdx.x] = (red[0] + red[2]) + (red[4] + red[6]);
     d.partials[kMaxPartials + blockIdx.x] = (red[1] + red[3]) + (red[5] + red[7]);
@@ -1169,9 +1176,12 @@ __global__ void __launch_bounds__(kThreadsT, 1)
       }
       record_scale(d, s.out_slot, norm, s.out_numel);
       d.tickets[s.ticket] = 0;
+      trace_wall(launch_flags, 2);
+      trace_wall(launch_flags, 3, (long long)blockIdx.x);
     }
   }
   if (warp == 12) trace(launch_flags, 31, 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_wall(launch_flags, 1);
 }
 
 static int pick_layout4(const GemmMode* rows, int n_rows, const GemmMode* ks, int n_k, bool use_b) {

@@ -22,8 +22,9 @@ for _ in range(3):
     plan.execute_device(ops)
 torch.cuda.synchronize()
 lib.ctn_debug_t32_trace(buf, E * I)  # drop the warm-up records
-plan.execute_device(ops)
+_, _, ms = plan.execute_device(ops, timed=True)
 torch.cuda.synchronize()
+print("launch durations by CUDA events (us):", [round(x * 1e3, 1) for x in ms], plan.launch_kinds)
 lib.ctn_debug_t32_trace(buf, E * I)
 t = np.array(buf[:], dtype=np.int64).reshape(E, I)
 names = {0: "start", 1: "A raw landed", 2: "A tmem free", 3: "FullA", 4: "issued", 5: "B landed", 6: "FullB",
@@ -49,6 +50,20 @@ if t[11, 1] > 0:  # inside the A converters: landed -> stage free -> FullA -> [p
     for it in range(8, min(n_it - 1, 16)):
         print(f"{it:4d}  {int(t[2, it] - t[1, it]):6d} {int(t[3, it] - t[2, it]):6d} {int(t[11, it] - t[3, it]):6d} "
               f"{int(t[18, it] - t[11, it]):6d} {int(t[19, it] - t[18, it]):6d} {int(t[25, it] - t[19, it]):6d} {int(t[1, it + 1] - t[25, it]):6d}")
+if t[29, 0] > 0:
+    print(f"wall clock (ns): CTA 0 enter -> leave {int(t[29, 1] - t[29, 0])}; CTA 0 enter -> last CTA (block {int(t[29, 3])}) recorded the "
+          f"scale {int(t[29, 2] - t[29, 0])}; CTA 0's cycle span start->end {int(t[31, 0] - t0)}")
+if t[18, 0] > 0:
+    print(f"set-up (cycles before 'start'): entry {int(t[18, 0] - t0)}, barriers initialised {int(t[18, 1] - t0)}, TMEM allocated {int(t[18, 2] - t0)}")
+if t[19, 0] > 0:
+    nb = int((t[19] > 0).sum())
+    ent = (t[19, :nb] - t[29, 0]) / 1e3
+    lea = (t[25, :nb] - t[29, 0]) / 1e3
+    print(f"{nb} CTAs: entry (us after CTA 0's) min {ent.min():.2f} median {np.median(ent):.2f} max {ent.max():.2f}; roles done min {lea.min():.2f} "
+          f"median {np.median(lea):.2f} max {lea.max():.2f}; busy time min {(lea - ent).min():.2f} median {np.median(lea - ent):.2f} max {(lea - ent).max():.2f}")
+    order = np.argsort(lea)
+    print("   slowest CTAs (block: entry, done):", [(int(b), round(float(ent[b]), 2), round(float(lea[b]), 2)) for b in order[-6:]])
+    print("   fastest CTAs (block: entry, done):", [(int(b), round(float(ent[b]), 2), round(float(lea[b]), 2)) for b in order[:6]])
 d = np.diff(t[9, :n_it])
 if len(d) > 4:
     print("cycles between consecutive 'mma issued': median", int(np.median(d)), "mean", int(d.mean()))
