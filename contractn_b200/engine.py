@@ -474,15 +474,35 @@ def _run_numpy(arrays, contraction_list, out_mode=CTN_OUT_SPLIT):
     return out, np.array(log_scale, dtype=np.float64)
 
 
+_AUTOGRAD_FN = None
+
+
+def _contract_split_nograd(einstr, *operands):
+    import torch
+
+    with torch.no_grad():
+        return contract(einstr, *operands, split_format=True)
+
+
 def _run_torch(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
+    """torch tensors in, torch tensors out.  Operands that require gradients go through
+    ``autograd.ContractFn`` (the reference's torch backend is differentiable plain torch ops,
+    einsum.py:326-393): the backward is one more stabilised contraction per such operand."""
     import torch
 
     if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
-        # the reference's torch backend is plain differentiable torch ops; this engine has no
-        # backward plan, and silently detaching would hand a training loop zero gradients
-        raise NotImplementedError(
-            "contractn_b200 has no autograd through the device plan: call under torch.no_grad() "
-            "or pass detached tensors")
+        global _AUTOGRAD_FN
+        if _AUTOGRAD_FN is None:
+            from . import autograd
+
+            _AUTOGRAD_FN = autograd.make_function(_run_torch_nograd, _contract_split_nograd)
+        return _AUTOGRAD_FN.apply(contraction_list, out_mode, out_mode == CTN_OUT_DENSE, *tensors)
+    return _run_torch_nograd(tensors, contraction_list, out_mode)
+
+
+def _run_torch_nograd(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
+    import torch
+
     if not tensors[0].is_cuda:
         out, log_scale = _run_numpy([t.detach().numpy() for t in tensors], contraction_list, out_mode)
         res = torch.from_numpy(np.ascontiguousarray(out))

@@ -5,16 +5,6 @@ import pytest
 from contractn_b200 import engine, networks, planner
 
 
-def test_requires_grad_is_refused_not_silently_detached():
-    """The reference's torch backend is differentiable plain torch ops (einsum.py:326-393); this engine has
-    no backward plan, so tensors that ask for gradients must raise instead of being detached."""
-    torch = pytest.importorskip("torch")
-    a = torch.rand(4, 5, requires_grad=True)
-    b = torch.rand(5, 6)
-    with pytest.raises(NotImplementedError):
-        engine.contract("ab,bc->ac", a, b, split_format=True)
-
-
 def test_unknown_kwargs_raise_like_the_reference():
     with pytest.raises(TypeError):
         engine.contract("ab,bc->ac", np.ones((2, 3)), np.ones((3, 4)), bogus=1)  # einsum.py:286-290
