@@ -220,3 +220,20 @@ def test_cfg2_full_size_properties(gpu_engine):
     np.testing.assert_allclose(T, wT, rtol=1e-12)
     assert abs(c - wc) < 1e-9
     assert abs(np.abs(T).mean() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_batched_mps_under_the_default_optimizer(gpu_engine, dtype):
+    """cfg 3's network at a size where ``optimize="auto"`` is runnable (at literal size its greedy path needs
+    1e157 elements, benchmarks/cfg3_greedy_path.py): default optimiser and explicit sweep give the oracle's
+    result, each on its own path."""
+    from contractn_b200 import networks
+
+    tn, sweep = networks.mps_tn(sites=6, bond=8, phys=2, batch=16, dtype=dtype, seed=9)
+    ops = [np.asarray(p) for p in tn.params]
+    shapes = tuple(o.shape for o in ops)
+    for opt in ("auto", sweep):
+        lst = planner.contract_path(tn.einsum_str, *shapes, optimize=opt)[1]
+        T, c = gpu_engine.core_contract(ops, lst)
+        rT, rc = oracle.core_contract(ops, lst)
+        assert_split_close(T, c, rT, rc, dtype == np.float32, False, what="mps/%s" % (opt if opt == "auto" else "sweep"))
