@@ -400,11 +400,12 @@ def run_multi_gpu_records(world, rank, dev):
 
     from contractn_b200 import engine, networks, parallel, planner
 
-    def timed(fn, reps=2):
+    def timed(fn, reps=2, free=True):
         best, res = None, None
         for _ in range(reps):
             res = None  # (release the previous result first: a tier-L slab is 68.7 GB)
-            torch.cuda.empty_cache()
+            if free:  # tier L needs the memory back; otherwise the caching allocator keeps the blocks (a cudaMalloc
+                torch.cuda.empty_cache()  # of gigabytes inside the timed region is not part of the contraction)
             dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -422,7 +423,8 @@ def run_multi_gpu_records(world, rank, dev):
         tn, opt = networks.cp_tn(I, R)
         einstr = tn.einsum_str
         fs = [torch.as_tensor(p).to(dev) for p in tn.params]
-        sec, (T, c, (lo, hi)) = timed(lambda: parallel.contract_output_slabs(einstr, *fs, optimize=opt))
+        sec, (T, c, (lo, hi)) = timed(lambda: parallel.contract_output_slabs(einstr, *fs, optimize=opt),
+                                      reps=2 if I == 4096 else 4, free=I == 4096)
         rng = np.random.default_rng(40 + rank)
         idx = np.stack([rng.integers(lo, hi, 2000), rng.integers(0, I, 2000), rng.integers(0, I, 2000)], axis=1)
         terms = einstr.split("->")[0].split(",")
