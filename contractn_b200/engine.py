@@ -447,8 +447,45 @@ _BUNDLE_MAX_BYTES = 16 << 20
 _bundle = None
 
 
+def _run_with_empty_operands(operands, contraction_list, out_mode, runner, zeros):
+    """Operands with a zero extent (einsum.py:97-106: ``sum(abs(T))`` of an empty or all-zero tensor is 0, below
+    ``min_norm``, so such a step leaves the register alone).  The plan compiler has no kernels for empty tensors, so
+    the pairwise list is walked on the host: a step that touches an empty operand -- or the zeros that came out of
+    such a step -- yields zeros of its output shape and no scale; every other step is ONE device contraction through
+    ``runner`` (its operands are raw inputs or canonical results, so its log-scale is exactly what the reference's
+    ``stabilize`` would add at that step).  Only the list's bookkeeping happens here: no arithmetic on data."""
+    running = [(op, 0 in tuple(op.shape)) for op in operands]
+    log_scale = 0.0
+    for step in contraction_list:
+        inds, einsum_str = step[0], step[2]
+        popped = [running.pop(x) for x in sorted(inds, reverse=True)]
+        ins, out = einsum_str.split("->")
+        ins = ins.split(",")
+        if any(dead for _, dead in popped):
+            dims = {}
+            for (arr, _), lab in zip(popped, ins):
+                dims.update(zip(lab, tuple(arr.shape)))
+            running.append((zeros(tuple(dims[ch] for ch in out)), True))
+        else:
+            # the local one-step list pops its operands in descending position order (einsum.py:347): hand them
+            # over reversed so that they meet the step's einsum string in order
+            local = [(tuple(range(len(popped) - 1, -1, -1)), step[1], einsum_str, (out,), step[4])]
+            t, c = runner([arr for arr, _ in popped][::-1], local, CTN_OUT_SPLIT)
+            log_scale += float(c)
+            running.append((t, False))
+    (result, dead), = running
+    if not dead and out_mode == CTN_OUT_DENSE:  # (cannot happen with an empty operand in the list; kept for symmetry)
+        result = result * float(np.exp(log_scale))
+    return result, log_scale
+
+
 def _run_numpy(arrays, contraction_list, out_mode=CTN_OUT_SPLIT):
     global _bundle
+    if any(0 in np.shape(a) for a in arrays):
+        dtype = _compute_dtype({np.asarray(a).dtype for a in arrays})
+        out, log_scale = _run_with_empty_operands([np.asarray(a) for a in arrays], contraction_list, out_mode,
+                                                  _run_numpy, lambda shape: np.zeros(shape, dtype=dtype))
+        return np.asarray(out, dtype=dtype), np.array(log_scale, dtype=np.float64)
     b = _bundle
     if (b is not None and b[0] is contraction_list and len(arrays) == len(b[1])
             and all(map(operator.is_, arrays, b[1]))
@@ -511,6 +548,11 @@ def _run_torch_nograd(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
     if any(t.is_complex() for t in tensors):
         raise NotImplementedError("complex tensors are not supported by the B200 engine")
     tensors = [t.detach() for t in tensors]
+    if any(0 in tuple(t.shape) for t in tensors):
+        out, log_scale = _run_with_empty_operands(
+            tensors, contraction_list, out_mode, _run_torch_nograd,
+            lambda shape: torch.zeros(shape, dtype=tdt, device=tensors[0].device))
+        return out.to(tdt), torch.tensor(log_scale, dtype=tdt, device=tensors[0].device)
     tensors = [t if t.dtype == tdt else t.to(tdt) for t in tensors]
     tensors = [t if all(s >= 0 for s in t.stride()) else t.contiguous() for t in tensors]
     shapes = tuple(tuple(t.shape) for t in tensors)

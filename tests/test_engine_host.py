@@ -40,3 +40,26 @@ def test_tf32_plans_prefer_row_fastest_intermediates():
     fused = [ln for ln in text.splitlines() if "fuse_pr=2" in ln]
     assert len(fused) == 4, text
     assert all("out_strides=1,256" in ln for ln in fused[:-1]), text  # (the last site feeds a generic step)
+
+
+@pytest.mark.parametrize("einstr,shapes", [
+    ("ab,bc,cd->ad", [(3, 4), (4, 0), (0, 5)]),      # the empty index is summed: zeros of shape (3, 5)
+    ("ab,bc,cd->ad", [(3, 4), (4, 5), (5, 0)]),      # the empty index is kept: an empty (3, 0) result
+    ("ab,bc,cd,de->ae", [(3, 4), (4, 5), (5, 0), (0, 2)]),
+    ("ab,cd,be->acde", [(3, 4), (0, 2), (4, 5)]),
+])
+def test_empty_operands_walk_matches_the_oracle(einstr, shapes):
+    """Zero-extent operands (einsum.py:97-106: norm 0 is below min_norm, the register is left alone): the host walk
+    over the pairwise list must give the oracle's zeros AND its log-scale, which only the steps among non-empty
+    operands feed.  The device runner is replaced by the oracle here (no GPU): what is tested is the bookkeeping."""
+    from oracle import contract_oracle as oracle
+
+    rng = np.random.default_rng(3)
+    ops = [rng.uniform(0.5, 1.5, s) for s in shapes]
+    lst = planner.contract_path(einstr, *shapes)[1]
+    want_T, want_c = oracle.core_contract(ops, lst)
+    got_T, got_c = engine._run_with_empty_operands(
+        ops, lst, engine.CTN_OUT_SPLIT, lambda o, l, m: oracle.core_contract(o, l), lambda shape: np.zeros(shape))
+    assert np.asarray(got_T).shape == np.asarray(want_T).shape
+    assert not np.any(np.asarray(got_T))
+    assert abs(float(got_c) - float(want_c)) < 1e-12

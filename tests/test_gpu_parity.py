@@ -237,3 +237,28 @@ def test_batched_mps_under_the_default_optimizer(gpu_engine, dtype):
         T, c = gpu_engine.core_contract(ops, lst)
         rT, rc = oracle.core_contract(ops, lst)
         assert_split_close(T, c, rT, rc, dtype == np.float32, False, what="mps/%s" % (opt if opt == "auto" else "sweep"))
+
+
+@pytest.mark.parametrize("einstr,shapes", [
+    ("ab,bc,cd->ad", [(30, 40), (40, 0), (0, 50)]),
+    ("ab,bc,cd->ad", [(30, 40), (40, 50), (50, 0)]),
+    ("ab,bc,cd,de->ae", [(30, 40), (40, 50), (50, 0), (0, 20)]),
+])
+def test_zero_extent_operands(gpu_engine, einstr, shapes):
+    """einsum.py:97-106 with empty tensors: zeros (or an empty result) and the log-scale of the steps among the
+    non-empty operands, numpy and torch, split and dense."""
+    import torch
+
+    rng = np.random.default_rng(4)
+    ops = [rng.uniform(0.5, 1.5, s) for s in shapes]
+    lst = planner.contract_path(einstr, *shapes)[1]
+    with np.errstate(invalid="ignore"):
+        want_T, want_c = oracle.core_contract(ops, lst)
+    T, c = gpu_engine.core_contract(ops, lst)
+    assert T.shape == want_T.shape and T.dtype == want_T.dtype and not np.any(T)
+    assert abs(float(c) - float(want_c)) < 1e-9
+    dense = gpu_engine.contract(einstr, *ops)
+    assert dense.shape == want_T.shape and not np.any(dense)
+    tT, tc = gpu_engine.core_contract([torch.as_tensor(o).cuda() for o in ops], lst)
+    assert tuple(tT.shape) == want_T.shape and tT.is_cuda and not bool(tT.any())
+    assert abs(float(tc) - float(want_c)) < 1e-9
