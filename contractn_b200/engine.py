@@ -479,8 +479,41 @@ def _run_with_empty_operands(operands, contraction_list, out_mode, runner, zeros
     return result, log_scale
 
 
+def _run_complex_numpy(arrays, contraction_list, out_mode):
+    import math
+
+    from . import complex_lowering as cl
+
+    arrays = [np.asarray(a) for a in arrays]
+    single = np.result_type(*[a.dtype for a in arrays]) == np.complex64
+    rdt, cdt = (np.float32, np.complex64) if single else (np.float64, np.complex128)
+
+    def to_real(x):
+        x = np.ascontiguousarray(x, dtype=cdt)
+        return x.view(rdt).reshape(x.shape + (2,))
+
+    def to_complex(x):
+        x = np.ascontiguousarray(x, dtype=rdt)
+        return x.view(cdt).reshape(x.shape[:-1])
+
+    def modulus_mean(x):
+        tot = float(np.abs(x).sum(dtype=np.float64))
+        return tot, tot / max(x.size, 1)
+
+    out, log_scale = cl.run(arrays, contraction_list, lambda e, *o, **k: contract(e, *o, split_format=True, **k),
+                            to_real, cl.structure_tensor(rdt), to_complex, modulus_mean, math.log)
+    if out_mode == CTN_OUT_DENSE:
+        with np.errstate(over="ignore", invalid="ignore"):
+            out = out * np.exp(log_scale)
+    return out.astype(cdt, copy=False), np.array(log_scale, dtype=np.float64)
+
+
 def _run_numpy(arrays, contraction_list, out_mode=CTN_OUT_SPLIT):
     global _bundle
+    if any(np.iscomplexobj(a) for a in arrays):
+        if any(0 in np.shape(a) for a in arrays):
+            raise NotImplementedError("complex operands with a zero extent")
+        return _run_complex_numpy(arrays, contraction_list, out_mode)
     if any(0 in np.shape(a) for a in arrays):
         dtype = _compute_dtype({np.asarray(a).dtype for a in arrays})
         out, log_scale = _run_with_empty_operands([np.asarray(a) for a in arrays], contraction_list, out_mode,
@@ -528,6 +561,8 @@ def _run_torch(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
     import torch
 
     if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        if any(t.is_complex() for t in tensors):
+            raise NotImplementedError("autograd through a contraction of complex tensors")
         global _AUTOGRAD_FN
         if _AUTOGRAD_FN is None:
             from . import autograd
@@ -537,16 +572,44 @@ def _run_torch(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
     return _run_torch_nograd(tensors, contraction_list, out_mode)
 
 
+def _run_complex_torch(tensors, contraction_list, out_mode):
+    import math
+
+    import torch
+
+    from . import complex_lowering as cl
+
+    single = all(t.dtype in (torch.complex64, torch.float32, torch.float16) for t in tensors)
+    rdt, cdt = (torch.float32, torch.complex64) if single else (torch.float64, torch.complex128)
+    dev = tensors[0].device
+
+    def modulus_mean(x):
+        tot = float(x.abs().sum(dtype=torch.float64))
+        return tot, tot / max(x.numel(), 1)
+
+    with torch.no_grad():
+        out, log_scale = cl.run(
+            [t.detach() for t in tensors], contraction_list,
+            lambda e, *o, **k: contract(e, *o, split_format=True, **k),
+            lambda x: torch.view_as_real(x.to(cdt).contiguous()),
+            torch.as_tensor(cl.structure_tensor(np.float32 if single else np.float64), device=dev),
+            lambda x: torch.view_as_complex(x.to(rdt).contiguous()), modulus_mean, math.log)
+        if out_mode == CTN_OUT_DENSE:
+            out = out * torch.exp(torch.tensor(log_scale, dtype=torch.float64, device=dev)).to(rdt)
+    return out, torch.tensor(log_scale, dtype=rdt, device=dev)
+
+
 def _run_torch_nograd(tensors, contraction_list, out_mode=CTN_OUT_SPLIT):
     import torch
 
     if not tensors[0].is_cuda:
         out, log_scale = _run_numpy([t.detach().numpy() for t in tensors], contraction_list, out_mode)
         res = torch.from_numpy(np.ascontiguousarray(out))
-        return res, torch.tensor(float(log_scale), dtype=res.dtype)
+        return res, torch.tensor(float(log_scale), dtype=torch.float32 if res.dtype in (torch.float32, torch.complex64)
+                                 else torch.float64)
     tdt = torch.float64 if any(t.dtype == torch.float64 for t in tensors) else torch.float32
     if any(t.is_complex() for t in tensors):
-        raise NotImplementedError("complex tensors are not supported by the B200 engine")
+        return _run_complex_torch(tensors, contraction_list, out_mode)
     tensors = [t.detach() for t in tensors]
     if any(0 in tuple(t.shape) for t in tensors):
         out, log_scale = _run_with_empty_operands(
@@ -620,6 +683,8 @@ def contract(*operands, **kwargs):
         ops = [np.asarray(o, dtype=einsum_kwargs["dtype"]) for o in ops]
     if _is_torch(ops[0]):
         return _run_torch(ops, contract_list, CTN_OUT_DENSE)[0]
+    if any(np.iscomplexobj(a) for a in ops):
+        return _run_numpy(ops, contract_list, CTN_OUT_DENSE)[0]
     dtype = _compute_dtype({np.asarray(a).dtype for a in ops})
     if dtype == np.float32:
         # numpy's own rule for float32 array * 0-d float64 register (einsum.py:114, 338) is a float64
