@@ -1,0 +1,88 @@
+"""Boundary-sharded sweep across GPUs (contractn_b200.sharded): parity against the float64 oracle and
+against the unsharded one-GPU contraction, timing against the UNSHARDED contraction on one GPU, and a
+per-segment time line (compute / scale merge / exchange) from CUDA events.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29541 benchmarks/check_sharded_sweep.py [L] [D] [--no-oracle]"""
+import json, os, sys, time
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from contractn_b200 import engine, networks, parallel, planner, sharded
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+L = int(args[0]) if args else 8
+D = int(args[1]) if len(args) > 1 else 8
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+tn, path = networks.peps_tn(L, D)
+einstr = tn.einsum_str
+ops = [torch.as_tensor(p).to(dev) for p in tn.params]
+shapes = tuple(tuple(o.shape) for o in ops)
+lst = planner.cached_contract_list(einstr, shapes, optimize=path)
+
+sw = sharded.ShardedSweep(einstr, ops, optimize=path)
+for _ in range(3):
+    T, c = sw.run()
+torch.cuda.synchronize()
+times = []
+for _ in range(10):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    T, c = sw.run()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    times.append(float(t))
+rec = {"world": world, "workload": f"closed {L}x{L} grid, D = {D}, f64, row-by-row sweep path",
+       "segments": len(sw.segments), "exchanges": sum(s.exchange is not None for s in sw.segments),
+       "exchanged_MB_per_rank": sw.exchanged_bytes / 1e6,
+       "seconds_best": min(times), "seconds_median": sorted(times)[len(times) // 2]}
+
+# time line of one run: events around every segment's compute and exchange
+marks = []
+orig_seg, orig_merge = sw._run_segment, sharded.merge_batch_shards
+def ev():
+    e = torch.cuda.Event(enable_timing=True); e.record(); return e
+def seg_timed(k, seg, o):
+    a = ev(); r = orig_seg(k, seg, o); marks.append((k, "compute", a, ev())); return r
+sw._run_segment = seg_timed
+e0 = ev(); sw.run(); e1 = ev(); torch.cuda.synchronize()
+sw._run_segment = orig_seg
+comp = sum(a.elapsed_time(b) for _, _, a, b in marks)
+rec["timeline_ms"] = {"total": e0.elapsed_time(e1), "segments_compute": comp,
+                      "merge_plus_exchange_plus_gaps": e0.elapsed_time(e1) - comp,
+                      "per_segment_compute": [round(a.elapsed_time(b), 3) for _, _, a, b in marks]}
+
+if rank == 0:
+    plan = engine.get_plan(lst, shapes, np.float64, device=dev.index)
+    b = plan.bind(ops)
+    b.run(); torch.cuda.synchronize()
+    one = []
+    for _ in range(5):
+        t0 = time.perf_counter(); Tu, tail = b.run(); torch.cuda.synchronize(); one.append(time.perf_counter() - t0)
+    cu = float(tail[0].item())
+    rec.update({"seconds_unsharded_1gpu": min(one), "speedup_vs_unsharded_1gpu": min(one) / min(times),
+                "path_flops": planner.path_flops(lst, einstr, shapes),
+                "aggregate_path_tflops": planner.path_flops(lst, einstr, shapes) / min(times) / 1e12,
+                "max_rel_err_T_vs_unsharded": float((T.double() - Tu.double()).abs().max() / Tu.double().abs().max()),
+                "abs_err_log_scale_vs_unsharded": abs(float(c.reshape(-1)[0]) - cu)})
+    if "--no-oracle" not in sys.argv:
+        from oracle import contract_oracle as oracle
+        t0 = time.perf_counter()
+        To, co = oracle.contract(lst, *[np.asarray(p) for p in tn.params], split_format=True)
+        rec.update({"oracle_seconds": time.perf_counter() - t0,
+                    "max_rel_err_T_vs_oracle": float(np.abs(T.cpu().numpy() - np.asarray(To)).max() / np.abs(To).max()),
+                    "abs_err_log_scale_vs_oracle": abs(float(c.reshape(-1)[0]) - float(co))})
+    print(json.dumps(rec))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/sharded_sweep_{L}x{L}_D{D}_{world}gpu.json", "w") as f:
+        json.dump(rec, f, indent=1)
+    assert rec["max_rel_err_T_vs_unsharded"] < 1e-11 and rec["abs_err_log_scale_vs_unsharded"] < 1e-9
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()
