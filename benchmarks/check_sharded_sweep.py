@@ -51,13 +51,28 @@ def ev():
     e = torch.cuda.Event(enable_timing=True); e.record(); return e
 def seg_timed(k, seg, o):
     a = ev(); r = orig_seg(k, seg, o); marks.append((k, "compute", a, ev())); return r
-sw._run_segment = seg_timed
+def merge_timed(*a, **k):
+    x = ev(); r = orig_merge(*a, **k); marks.append((-1, "merge", x, ev())); return r
+orig_a2a, orig_ag = dist.all_to_all_single, dist.all_gather_into_tensor
+def a2a_timed(*a, **k):
+    x = ev(); r = orig_a2a(*a, **k); marks.append((-1, "a2a", x, ev())); return r
+def ag_timed(*a, **k):
+    x = ev(); r = orig_ag(*a, **k); marks.append((-1, "gather", x, ev())); return r
+sw._run_segment = seg_timed; sharded.merge_batch_shards = merge_timed
+dist.all_to_all_single = a2a_timed; dist.all_gather_into_tensor = ag_timed
 e0 = ev(); sw.run(); e1 = ev(); torch.cuda.synchronize()
-sw._run_segment = orig_seg
-comp = sum(a.elapsed_time(b) for _, _, a, b in marks)
-rec["timeline_ms"] = {"total": e0.elapsed_time(e1), "segments_compute": comp,
-                      "merge_plus_exchange_plus_gaps": e0.elapsed_time(e1) - comp,
-                      "per_segment_compute": [round(a.elapsed_time(b), 3) for _, _, a, b in marks]}
+sw._run_segment = orig_seg; sharded.merge_batch_shards = orig_merge
+dist.all_to_all_single = orig_a2a; dist.all_gather_into_tensor = orig_ag
+tot = lambda kind: sum(a.elapsed_time(b) for _, k, a, b in marks if k == kind)
+rec["timeline_ms"] = {"total": e0.elapsed_time(e1), "segments_compute": tot("compute"), "scale_merges": tot("merge"),
+                      "all_to_all": tot("a2a"), "all_gather": tot("gather"),
+                      "per_segment_compute": [round(a.elapsed_time(b), 3) for _, k, a, b in marks if k == "compute"],
+                      "per_all_to_all": [round(a.elapsed_time(b), 3) for _, k, a, b in marks if k == "a2a"]}
+ks = 3 if len(sw.segments) > 3 else 0
+hit = sw._bound[ks]
+_, _, ms = hit[2].execute_device(hit[1].tensors, out=hit[1].out, timed=True)
+rec["segment_kernels"] = {"segment": ks, "einsum": sw.segments[ks].einstr(), "ms": [round(m, 4) for m in ms],
+                          "plan": hit[2].describe().splitlines()}
 
 if rank == 0:
     plan = engine.get_plan(lst, shapes, np.float64, device=dev.index)

@@ -153,6 +153,7 @@ struct Plan {
   std::vector<int32_t> slot_list;  // chain inputs
   std::vector<Launch> launches;
   int32_t final_slot = -1;
+  bool raw_final = false;  // CTN_PLAN_RAW_FINAL honoured: no finalize launch, output = T-hat * kappa[final_slot]
   int32_t n_tickets = 0;
   double flops = 0;
   StateLayout state;
@@ -201,6 +202,9 @@ constexpr int kMailboxMaxWorld = 64;   // ranks per peer mailbox (CTN_MAILBOX_WO
 cudaError_t launch_merge_shards_peer(void* data, int64_t numel, int dtype, const StateHdr* hdr, double* const* mailboxes,
                                      int world, int rank, unsigned long long seq, double* log_scale_out,
                                      cudaStream_t stream);
+cudaError_t launch_reshard_peer(const void* data, int64_t numel, int dtype, const StateHdr* hdr, const double* kappa_raw,
+                                double* const* mailboxes, double* const* done_boxes, void* const* recv, uint32_t* ticket,
+                                int world, int rank, unsigned long long seq, double* log_scale_out, cudaStream_t stream);
 cudaError_t launch_merge_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                                 double* log_scale_out, cudaStream_t stream);
 cudaError_t launch_generic(const ExecCtx& c, const Launch& l);

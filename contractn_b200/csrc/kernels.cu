@@ -1058,6 +1058,150 @@ cudaError_t launch_merge_shards_peer(void* data, int64_t numel, int dtype, const
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// multi-GPU: scale merge + all-to-all re-sharding of a boundary slab in ONE kernel over peer memory
+// (contractn_b200/sharded.py).  Triple exchange as in merge_shards_peer_kernel; then every element is
+// read ONCE from the local slab, multiplied by the common-scale factor (and by 1/kappa_raw when the
+// producing plan skipped its finalize pass) and stored straight into the destination rank's receive
+// buffer over NVLink: chunk j of [world][chunk] goes to recv[j] + rank * chunk.  blockIdx.y is the
+// destination, so every link is busy at once and each CTA streams one contiguous range.  The last CTA
+// to finish tells every peer "my stores have landed" (release flag after a system fence) and waits for
+// the peers' flags: kernel completion on a rank means its receive buffer is complete.
+// ---------------------------------------------------------------------------
+struct PeerPtrs {
+  void* p[kMailboxMaxWorld];
+};
+
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<double> {
+  using type = double2;
+  static __device__ __forceinline__ double2 mul(double2 v, double s) { return make_double2(v.x * s, v.y * s); }
+};
+template <>
+struct Vec16<float> {
+  using type = float4;
+  static __device__ __forceinline__ float4 mul(float4 v, double s) {
+    const float f = (float)s;
+    return make_float4(v.x * f, v.y * f, v.z * f, v.w * f);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) reshard_peer_kernel(const T* __restrict__ src, int64_t chunk,
+                                                                const StateHdr* __restrict__ hdr,
+                                                                const double* __restrict__ kappa_raw, PeerBoxes boxes,
+                                                                PeerBoxes done, PeerPtrs recv, unsigned int* ticket,
+                                                                int world, int rank, unsigned long long seq,
+                                                                double* log_scale_out, int vec) {
+  __shared__ double tab[3 * kMailboxMaxWorld];
+  __shared__ int give_up, is_last;
+  const int par = (int)(seq & 1ull);
+  const double seq_d = (double)seq;
+  const bool first = blockIdx.x == 0 && blockIdx.y == 0;
+  if (first && threadIdx.x < world) {
+    double* slot = boxes.p[threadIdx.x] + ((size_t)par * world + rank) * 4;
+    slot[0] = hdr->log_scale;
+    slot[1] = hdr->final_abs;
+    slot[2] = (double)(chunk * world);
+    __threadfence_system();
+    st_release_sys(slot + 3, seq_d);
+  }
+  if (threadIdx.x == 0) give_up = 0;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const double* slot = boxes.p[rank] + ((size_t)par * world + threadIdx.x) * 4;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(slot + 3) != seq_d) {
+      if (clock64() - t0 > 20000000000LL) {
+        give_up = 1;
+        break;
+      }
+    }
+    tab[3 * threadIdx.x] = slot[0];
+    tab[3 * threadIdx.x + 1] = slot[1];
+    tab[3 * threadIdx.x + 2] = slot[2];
+  }
+  __syncthreads();
+  double c_star = -INFINITY;
+  for (int i = 0; i < world; ++i) c_star = fmax(c_star, tab[3 * i]);
+  double S = 0.0, N = 0.0;
+  for (int i = 0; i < world; ++i) {  // fixed order: every rank computes the same bits
+    S += tab[3 * i + 1] * exp(tab[3 * i] - c_star);
+    N += tab[3 * i + 2];
+  }
+  const double kappa = S / N;
+  double scale = give_up ? __longlong_as_double(0x7ff8000000000000LL) : exp(tab[3 * rank] - c_star) / kappa;
+  if (kappa_raw) scale /= *kappa_raw;
+  const int j = blockIdx.y;  // destination rank
+  const T* s = src + (int64_t)j * chunk;
+  T* d = (T*)recv.p[j] + (int64_t)rank * chunk;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    using V = typename Vec16<T>::type;
+    constexpr int E = 16 / (int)sizeof(T);
+    const V* sv = (const V*)s;
+    V* dv = (V*)d;
+    const int64_t n = chunk / E;
+    int64_t i = tid;
+    for (; i + 3 * stride < n; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+      V a = sv[i], b = sv[i + stride], c = sv[i + 2 * stride], e = sv[i + 3 * stride];
+      dv[i] = Vec16<T>::mul(a, scale);
+      dv[i + stride] = Vec16<T>::mul(b, scale);
+      dv[i + 2 * stride] = Vec16<T>::mul(c, scale);
+      dv[i + 3 * stride] = Vec16<T>::mul(e, scale);
+    }
+    for (; i < n; i += stride) dv[i] = Vec16<T>::mul(sv[i], scale);
+  } else {
+    for (int64_t i = tid; i < chunk; i += stride) d[i] = (T)((double)s[i] * scale);
+  }
+  if (first && threadIdx.x == 0) *log_scale_out = give_up ? scale : c_star + log(kappa);
+  // completion: all my stores -> system fence -> ticket; the last CTA posts the flags and waits for the peers'
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence_system();
+  if (threadIdx.x < world) {
+    st_release_sys(done.p[threadIdx.x] + (size_t)par * world + rank, seq_d);
+    const double* flag = done.p[rank] + (size_t)par * world + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) != seq_d)
+      if (clock64() - t0 > 20000000000LL) break;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+cudaError_t launch_reshard_peer(const void* data, int64_t numel, int dtype, const StateHdr* hdr, const double* kappa_raw,
+                                double* const* mailboxes, double* const* done_boxes, void* const* recv, uint32_t* ticket,
+                                int world, int rank, unsigned long long seq, double* log_scale_out, cudaStream_t stream) {
+  PeerBoxes boxes, done;
+  PeerPtrs rp;
+  for (int i = 0; i < kMailboxMaxWorld; ++i) {
+    boxes.p[i] = i < world ? mailboxes[i] : nullptr;
+    done.p[i] = i < world ? done_boxes[i] : nullptr;
+    rp.p[i] = i < world ? recv[i] : nullptr;
+  }
+  const int64_t chunk = numel / world;
+  const size_t elem = dtype == CTN_F32 ? 4 : 8;
+  bool vec = (chunk * elem) % 16 == 0 && ((uintptr_t)data % 16) == 0;
+  for (int i = 0; i < world; ++i) vec = vec && ((uintptr_t)recv[i] % 16) == 0;
+  const int64_t per = vec ? 16 / (int64_t)elem : 1;
+  const int64_t blocks = (chunk / per + kThreads - 1) / kThreads;
+  const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (148 * 8 + world - 1) / world));
+  dim3 grid(gx, world);
+  if (dtype == CTN_F32)
+    reshard_peer_kernel<float><<<grid, kThreads, 0, stream>>>((const float*)data, chunk, hdr, kappa_raw, boxes, done, rp,
+                                                              ticket, world, rank, seq, log_scale_out, vec ? 1 : 0);
+  else
+    reshard_peer_kernel<double><<<grid, kThreads, 0, stream>>>((const double*)data, chunk, hdr, kappa_raw, boxes, done, rp,
+                                                               ticket, world, rank, seq, log_scale_out, vec ? 1 : 0);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                                 double* log_scale_out, cudaStream_t stream) {
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((numel + kThreads - 1) / kThreads, 148 * 8));

@@ -705,7 +705,8 @@ static int build_plan(const ctn_plan_desc& d, Plan& p, const LayoutOverrides* ov
   const StepDev& last_step = p.steps[last.last_step];
   (void)last_step;
   bool self_final = last.kind == kInterp || last.kind == kMaterialize;
-  if (!self_final) {
+  p.raw_final = !self_final && (p.flags & CTN_PLAN_RAW_FINAL);
+  if (!self_final && !p.raw_final) {
     int64_t bytes = 2 * p.slots[p.final_slot].numel * (int64_t)p.elem;
     p.launches.push_back(Launch{kFinalize, last.last_step, last.last_step, bytes, 0.0, 0});
   }
@@ -922,6 +923,11 @@ int64_t ctn_plan_output_numel(const ctn_plan* plan) {
   return plan ? plan->p.slots[plan->p.final_slot].numel : -1;
 }
 
+int64_t ctn_plan_final_kappa_offset(const ctn_plan* plan) {
+  if (!plan || !plan->p.raw_final) return -1;
+  return (int64_t)(plan->p.state.kappa + (size_t)plan->p.final_slot * sizeof(double));
+}
+
 int ctn_plan_num_launches(const ctn_plan* plan) {
   if (!plan) return -1;
   return (int)plan->p.launches.size();
@@ -1083,6 +1089,26 @@ int ctn_merge_batch_shards_peer(void* data, int64_t numel, int dtype, const void
                                            (unsigned long long)seq, log_scale_out, (cudaStream_t)stream);
   if (e != cudaSuccess) {
     set_cuda_error(e, "merge_shards_peer launch");
+    return CTN_ERR_CUDA;
+  }
+  return CTN_OK;
+}
+
+int ctn_reshard_peer(const void* data, int64_t numel, int dtype, const void* workspace, int64_t kappa_offset,
+                     double* const* mailboxes, double* const* done_boxes, void* const* recv, uint32_t* ticket,
+                     int world, int rank, uint64_t seq, double* log_scale_out, void* stream) {
+  if (!data || !workspace || !mailboxes || !done_boxes || !recv || !ticket || !log_scale_out || numel < 0)
+    return CTN_ERR_INVALID;
+  if (world < 1 || world > kMailboxMaxWorld || rank < 0 || rank >= world || seq == 0 || numel % world) return CTN_ERR_INVALID;
+  if (dtype != CTN_F32 && dtype != CTN_F64) return CTN_ERR_UNSUPPORTED;
+  for (int i = 0; i < world; ++i)
+    if (!mailboxes[i] || !done_boxes[i] || !recv[i]) return CTN_ERR_INVALID;
+  const double* kappa_raw = kappa_offset >= 0 ? (const double*)((const char*)workspace + kappa_offset) : nullptr;
+  cudaError_t e = launch_reshard_peer(data, numel, dtype, (const StateHdr*)workspace, kappa_raw, mailboxes, done_boxes,
+                                      recv, ticket, world, rank, (unsigned long long)seq, log_scale_out,
+                                      (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "reshard_peer launch");
     return CTN_ERR_CUDA;
   }
   return CTN_OK;

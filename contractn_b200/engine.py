@@ -34,6 +34,7 @@ CTN_OUT_SPLIT, CTN_OUT_DENSE = 0, 1
 CTN_PLAN_EXACT_STEPS = 1
 CTN_PLAN_NO_INTERPRETER = 2
 CTN_PLAN_NO_GEMM = 4
+CTN_PLAN_RAW_FINAL = 8
 CTN_RESULT_DEGENERATE = 1
 LAUNCH_KINDS = ("generic", "chain", "interp", "gemm", "finalize", "materialize", "gemm_reduce")
 
@@ -42,7 +43,8 @@ EXPORTS = (
     "ctn_plan_output_rank", "ctn_plan_output_extents", "ctn_plan_output_numel",
     "ctn_plan_num_launches", "ctn_plan_flops", "ctn_plan_step_bytes",
     "ctn_plan_launch_kind", "ctn_plan_describe", "ctn_plan_execute", "ctn_plan_execute_timed", "ctn_plan_execute_host",
-    "ctn_merge_batch_shards_peer", "ctn_merge_batch_shards", "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
+    "ctn_merge_batch_shards_peer", "ctn_merge_batch_shards", "ctn_reshard_peer", "ctn_plan_final_kappa_offset",
+    "ctn_status_string", "ctn_last_cuda_error", "ctn_abi_version", "ctn_device_count",
 )
 
 
@@ -126,6 +128,11 @@ def load_library():
         lib.ctn_merge_batch_shards_peer.argtypes = [vp, i64, ctypes.c_int, vp, ctypes.POINTER(vp), ctypes.c_int,
                                                     ctypes.c_int, ctypes.c_uint64, vp, vp]
         lib.ctn_merge_batch_shards_peer.restype = ctypes.c_int
+        lib.ctn_reshard_peer.argtypes = [vp, i64, ctypes.c_int, vp, i64, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                         ctypes.POINTER(vp), vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, vp, vp]
+        lib.ctn_reshard_peer.restype = ctypes.c_int
+        lib.ctn_plan_final_kappa_offset.argtypes = [vp]
+        lib.ctn_plan_final_kappa_offset.restype = i64
         lib.ctn_merge_batch_shards.argtypes = [vp, i64, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, vp]
         lib.ctn_merge_batch_shards.restype = ctypes.c_int
         lib.ctn_status_string.argtypes = [ctypes.c_int]
@@ -212,6 +219,7 @@ class Plan:
         _check(lib.ctn_plan_output_extents(handle, ext), "ctn_plan_output_extents")
         self.out_shape = tuple(int(ext[i]) for i in range(rank))
         self.workspace_bytes = int(lib.ctn_plan_workspace_bytes(handle))
+        self.final_kappa_offset = int(lib.ctn_plan_final_kappa_offset(handle))  # -1: output is canonical
         self.num_launches = int(lib.ctn_plan_num_launches(handle))
         self.flops = float(lib.ctn_plan_flops(handle))
         self.step_bytes = float(lib.ctn_plan_step_bytes(handle))

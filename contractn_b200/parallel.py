@@ -61,7 +61,8 @@ def _peer_state(dev, world, group):
                 torch.cuda.synchronize(dev)
                 dist.barrier(group=group)  # every mailbox is zeroed before anybody posts
                 st = {"box": box, "hdl": hdl, "ptrs": (ctypes.c_void_p * world)(*ptrs), "seq": 0,
-                      "c_out": torch.empty(1, dtype=torch.float64, device=dev)}
+                      "c_out": torch.empty(1, dtype=torch.float64, device=dev), "group": grp, "world": world,
+                      "arena": None}
             except Exception as exc:  # no symmetric memory on this platform / build
                 import warnings
 
@@ -69,6 +70,62 @@ def _peer_state(dev, world, group):
                 st = False
         _PEER[key] = st
     return st or None
+
+
+def peer_arena(st, nbytes):
+    """Peer-mapped receive arena of at least ``nbytes`` for the one-kernel re-sharding
+    (``ctn_reshard_peer``), plus the second mailbox through which the ranks report that their stores
+    have landed and the kernel's ticket word.  COLLECTIVE: every rank of the group calls it with the
+    same size.  Returns ``(arena tensor (uint8), [base pointer per rank])``."""
+    import ctypes
+
+    import torch.distributed._symmetric_memory as symm
+
+    from .engine import CTN_MAILBOX_WORDS
+
+    dev, world, grp = st["box"].device, st["world"], st["group"]
+    if "done" not in st:
+        done = symm.empty(CTN_MAILBOX_WORDS, dtype=torch.float64, device=dev)
+        done.zero_()
+        hdl = symm.rendezvous(done, grp)
+        st["done"], st["done_hdl"] = done, hdl
+        st["done_ptrs"] = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+        st["ticket"] = torch.zeros(4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=grp)
+    if st["arena"] is None or st["arena"][0].numel() < nbytes:
+        arena = symm.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(arena, grp)
+        st["arena"] = (arena, [int(p) for p in hdl.buffer_ptrs], hdl)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=grp)
+    return st["arena"][0], st["arena"][1]
+
+
+def reshard_peer(send, plan, st, arena_offset, group=None):
+    """ONE kernel: common-scale merge of the ranks' slabs and all-to-all over peer memory.  ``send`` is
+    this rank's slab ``[world][chunk]`` as ``plan`` (possibly a ``CTN_PLAN_RAW_FINAL`` one) left it; the
+    result is this rank's ``[world][chunk]`` receive buffer at ``arena_offset`` of the peer arena and the
+    common log-scale (a 1-element tensor that the next call overwrites)."""
+    import ctypes
+
+    from . import engine
+
+    lib = engine.load_library()
+    world = st["world"]
+    rank = dist.get_rank(group)
+    arena, bases = st["arena"][0], st["arena"][1]
+    nbytes = send.numel() * send.element_size()
+    assert arena_offset % 256 == 0 and arena_offset + nbytes <= arena.numel()
+    recv_ptrs = (ctypes.c_void_p * world)(*[b + arena_offset for b in bases])
+    dt = engine.CTN_F32 if send.dtype == torch.float32 else engine.CTN_F64
+    st["seq"] += 1
+    stream = torch.cuda.current_stream(send.device).cuda_stream
+    engine._check(lib.ctn_reshard_peer(send.data_ptr(), send.numel(), dt, plan._dev[2], plan.final_kappa_offset,
+                                       st["ptrs"], st["done_ptrs"], recv_ptrs, st["ticket"].data_ptr(), world, rank,
+                                       st["seq"], st["c_out"].data_ptr(), stream), "ctn_reshard_peer")
+    recv = arena[arena_offset:arena_offset + nbytes].view(send.dtype).view(send.shape)
+    return recv, st["c_out"]
 
 
 def merge_batch_shards(T_local, c_local, group=None, plan=None):

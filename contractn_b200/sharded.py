@@ -57,7 +57,8 @@ class _Segment:
         self.s2 = None              # next shard label (a2a)
         self.hi = None              # fresh symbol for the high part of s2 (a2a)
         self.out_id = None          # id under which the result (after the exchange) is stored
-        self.inputs = []            # external input ids, in order of first use
+        self.chain_in = None        # id of the sharded/running input (listed LAST, like the reference's sweep paths)
+        self.inputs = []            # external input ids, in order of first use (the chain input last)
         self.terms = []             # their labels as this segment's einsum sees them
         self.views = []             # per input: (slice_dim or None, split_dim or None)
         self.out = ""               # output labels of the segment's einsum
@@ -128,6 +129,11 @@ def plan_segments(einstr, shapes, contraction_list, world, min_numel=1 << 16):
             for i in ids:
                 if i not in made and i not in seg.inputs:
                     seg.inputs.append(i)
+        if seg.chain_in in seg.inputs:
+            # the running tensor goes last: the positional path then reads (k, 0), (k, 0), ... and the
+            # planner's step strings put the big operand first, as in the unsharded sweep
+            seg.inputs.remove(seg.chain_in)
+            seg.inputs.append(seg.chain_in)
         if exchange == "a2a":
             seg.hi = next(fresh)
         for i in seg.inputs:
@@ -185,14 +191,17 @@ def plan_segments(einstr, shapes, contraction_list, world, min_numel=1 << 16):
                     new = close(pending, "a2a" if s2 is not None else "gather", s2)
                     ids = tuple(new if i == old else i for i in ids)
                     pending = _Segment("shard", s2) if s2 is not None else _Segment("repl")
+                    pending.chain_in = new
                 pending.steps.append((ids, o))
                 pending.chain, pending.chain_labels = o, labels[o]
             else:
                 lab = labels[o]
                 s = pick(lab, removed) if numel(lab) >= min_numel else None
                 if s is not None:
+                    prev = pending.chain
                     close(pending)
                     pending = start(t, ids, o, removed)
+                    pending.chain_in = prev
                 else:
                     pending.steps.append((ids, o))
                     pending.chain, pending.chain_labels = o, lab
@@ -240,6 +249,25 @@ class ShardedSweep:
         self._bufs = {}
         self.dtype = torch.float64 if any(o.dtype == torch.float64 for o in self.operands) else torch.float32
         self.exchanged_bytes = 0
+        # CUDA, W > 1: the all-to-all exchanges are ONE kernel each over peer memory (scale merge fused, the
+        # producing plan's finalize pass skipped); otherwise merge kernel + NCCL/gloo all_to_all_single
+        self._peer = None
+        if self.world > 1 and contract_fn is None and self.operands[0].is_cuda:
+            from . import parallel
+
+            self._peer = parallel._peer_state(self.operands[0].device, self.world, group)
+            if self._peer is not None:
+                esz = 8 if self.dtype == torch.float64 else 4
+                size = {}
+                for t, shp in zip(_parse(einstr)[0], shapes):
+                    size.update(zip(t, shp))
+                need = [math.prod(self.world if ch == s.hi else size[ch] for ch in s.out) // self.world ** 2 * esz
+                        for s in self.segments if s.exchange == "a2a"]
+                # two halves, used alternately (one would do: a peer stores into my buffer only after my
+                # triple for THAT exchange is out, i.e. after I consumed the previous one)
+                self._half = (max(need, default=0) + 255) // 256 * 256
+                if need:
+                    parallel.peer_arena(self._peer, 2 * self._half)
 
     # -- one segment ---------------------------------------------------------------------------
     def _views(self, seg, store):
@@ -272,8 +300,9 @@ class ShardedSweep:
             strides = tuple(tuple(t.stride()) for t in ops)
             lst = planner.cached_contract_list(seg.einstr(), shapes, optimize=seg.path if seg.path else "auto")
             dev = ops[0].device
+            raw = engine.CTN_PLAN_RAW_FINAL if seg.exchange == "a2a" and self._peer is not None else 0
             plan = engine.get_plan(lst, shapes, np.float64 if self.dtype == torch.float64 else np.float32,
-                                   strides=strides, device=dev.index)
+                                   strides=strides, flags=raw, device=dev.index)
             out = torch.empty(plan.out_shape, dtype=self.dtype, device=dev)
             hit = (key, plan.bind(ops, out=out), plan)
             self._bound[k] = hit
@@ -293,19 +322,27 @@ class ShardedSweep:
         c_acc = None
         W = self.world
         self.exchanged_bytes = 0
-        out_id = None
+        out_id, n_a2a = None, 0
         for k, seg in enumerate(self.segments):
             out, c, plan = self._run_segment(k, seg, self._views(seg, store))
-            if seg.exchange is not None and W > 1:
+            fused = seg.exchange == "a2a" and self._peer is not None
+            if fused:
+                from . import parallel
+
+                n_a2a += 1
+                recv, c = parallel.reshard_peer(out, plan, self._peer, (n_a2a & 1) * self._half, group=self.group)
+                self.exchanged_bytes += out.numel() * out.element_size() * (W - 1) // W
+            elif seg.exchange is not None and W > 1:
                 out, c = merge_batch_shards(out, c, group=self.group, plan=plan)
             c_acc = c.clone() if c_acc is None else c_acc + c
             if seg.exchange == "a2a":
-                recv = self._buffer(k, out.shape, out)
-                if W > 1:
-                    dist.all_to_all_single(recv, out, group=self.group)
-                    self.exchanged_bytes += out.numel() * out.element_size() * (W - 1) // W
-                else:
-                    recv.copy_(out)
+                if not fused:
+                    recv = self._buffer(k, out.shape, out)
+                    if W > 1:
+                        dist.all_to_all_single(recv, out, group=self.group)
+                        self.exchanged_bytes += out.numel() * out.element_size() * (W - 1) // W
+                    else:
+                        recv.copy_(out)
                 # (s_hi, s_lo, s2_lo, rest) -> (s, s2_lo, rest): adjacent dims of a contiguous buffer
                 out = recv.reshape((recv.shape[0] * recv.shape[1],) + tuple(recv.shape[2:]))
             elif seg.exchange in ("gather", "final") and W > 1:

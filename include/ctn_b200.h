@@ -68,7 +68,12 @@ enum {
   /* Disable the single-CTA interpreter for runs of tiny steps. */
   CTN_PLAN_NO_INTERPRETER = 2,
   /* Disable the tiled tensor-core GEMM kernels (use the generic kernel). */
-  CTN_PLAN_NO_GEMM = 4
+  CTN_PLAN_NO_GEMM = 4,
+  /* Leave the result RAW: no finalize pass.  out = canonical T-hat times the pending scale kappa that
+   * sits in the workspace at ctn_plan_final_kappa_offset(); the log-scale in the state block already
+   * includes ln(kappa); *log_scale_out / *flags_out are NOT written.  For ctn_reshard_peer, which
+   * folds 1/kappa into the scale it applies while the data crosses NVLink. */
+  CTN_PLAN_RAW_FINAL = 8
 };
 
 /* output modes of ctn_plan_execute */
@@ -189,6 +194,26 @@ int ctn_merge_batch_shards_peer(void* data, int64_t numel, int dtype, const void
                                 double* log_scale_out, void* stream);
 int ctn_merge_batch_shards(void* data, int64_t numel, int dtype, const double* table, int world, int rank,
                            double* log_scale_out, void* stream);
+
+/* Byte offset, inside the workspace, of the double holding the pending scale kappa of a
+ * CTN_PLAN_RAW_FINAL plan's output; -1 when the output is already canonical (flag absent, or the last
+ * launch finalises by itself). */
+int64_t ctn_plan_final_kappa_offset(const ctn_plan* plan);
+
+/* Boundary-sharded sweep (contractn_b200/sharded.py; no reference counterpart: the reference is
+ * single-process): put this rank's slab on the common scale AND re-shard it across the ranks in ONE
+ * kernel over peer memory.  `data` is the slab as the producing plan left it, laid out
+ * [world][numel/world] with chunk j destined for rank j; `recv[i]` is rank i's receive buffer
+ * (numel elements, peer-mapped); chunk j is stored to recv[j] + rank * (numel/world), multiplied on
+ * the way by exp(c_rank - c*) / kappa (the ctn_merge_batch_shards_peer scale) and, when
+ * kappa_offset >= 0, by 1 / kappa_raw read from workspace + kappa_offset (a CTN_PLAN_RAW_FINAL
+ * plan).  `done_boxes[i]` is a second zeroed mailbox per rank (CTN_MAILBOX_WORDS doubles) through
+ * which the ranks tell one another that their stores have landed: when the kernel has completed on
+ * this rank, every peer's chunk is in recv[rank].  `ticket` is one zeroed uint32 in local device memory
+ * (left zero).  `seq` is shared with ctn_merge_batch_shards_peer (one counter per group). */
+int ctn_reshard_peer(const void* data, int64_t numel, int dtype, const void* workspace, int64_t kappa_offset,
+                     double* const* mailboxes, double* const* done_boxes, void* const* recv, uint32_t* ticket,
+                     int world, int rank, uint64_t seq, double* log_scale_out, void* stream);
 
 const char* ctn_status_string(int status);
 const char* ctn_last_cuda_error(void);
