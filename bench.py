@@ -494,7 +494,80 @@ def run_multi_gpu_records(world, rank, dev):
         out["sliced"] = rec
     except Exception as exc:
         out["sliced"] = {"error": f"{type(exc).__name__}: {exc}"}
+    # ---------------- boundary-sharded sweep (cfg 5, work stays 1x) ----------------
+    for L in ((8, 9) if world >= 4 else (8,)):
+        key = "sharded_sweep" if L == 8 else f"sharded_sweep_{L}x{L}"
+        try:
+            out[key] = sharded_sweep_record(L, 8, world, rank, dev)
+        except Exception as exc:
+            out[key] = {"error": f"{type(exc).__name__}: {exc}"}
+        engine.clear_plan_cache()
+        torch.cuda.empty_cache()
     return out
+
+
+def sharded_sweep_record(L, D, world, rank, dev):
+    """cfg 5 (closed L x L grid, bond D, f64, row-by-row sweep) with the boundary tensor SHARDED over one of its
+    legs (contractn_b200/sharded.py): every pairwise step of the path is executed once, 1/W of it per rank; the
+    boundary is re-sharded by one kernel over peer memory when the sharded leg is about to be absorbed.  Timed
+    against the UNSHARDED contraction on one GPU (same path, same plan as the N = 1 `cfg5` record)."""
+    import torch
+    import torch.distributed as dist
+
+    from contractn_b200 import engine, networks, planner, sharded
+
+    tn, path = networks.peps_tn(L, D)
+    einstr = tn.einsum_str
+    ops = [torch.as_tensor(p).to(dev) for p in tn.params]
+    shapes = tuple(tuple(o.shape) for o in ops)
+    lst = planner.cached_contract_list(einstr, shapes, optimize=path)
+    sw = sharded.ShardedSweep(einstr, ops, optimize=path)
+    for _ in range(2):
+        T, c = sw.run()
+    times = []
+    for _ in range(5 if L == 8 else 3):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        T, c = sw.run()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    flops = planner.path_flops(lst, einstr, shapes)
+    rec = {"workload": f"cfg5 tier: closed {L}x{L} grid, D = {D}, f64, row-by-row sweep; boundary sharded over a leg "
+                       f"on {world} GPUs", "seconds": min(times), "timing": "CUDA events, max over ranks, best of "
+                       f"{len(times)}", "work_multiplier": 1.0, "path_flops": flops,
+           "aggregate_path_tflops": flops / min(times) / 1e12,
+           "segments": len(sw.segments), "exchanges": sum(s.exchange is not None for s in sw.segments),
+           "exchanged_MB_per_rank": sw.exchanged_bytes / 1e6,
+           "exchange": "ctn_reshard_peer: scale merge + all-to-all stores over NVLink peer memory, one kernel"
+                       if sw._peer is not None else "merge kernel + NCCL all_to_all_single"}
+    c_mine = float(c.reshape(-1)[0].item())
+    T_mine = T.detach().double().cpu()
+    del sw
+    if rank == 0:
+        plan = engine.get_plan(lst, shapes, np.float64, device=dev.index)
+        b = plan.bind(ops)
+        b.run()
+        torch.cuda.synchronize()
+        one = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            Tu, tail = b.run()
+            e1.record()
+            torch.cuda.synchronize()
+            one.append(e0.elapsed_time(e1) / 1e3)
+        Tu = Tu.double().cpu()
+        rec.update({"seconds_unsharded_1gpu": min(one), "speedup_vs_unsharded_1gpu": min(one) / min(times),
+                    "max_rel_err_T_vs_unsharded": float((T_mine - Tu).abs().max() / Tu.abs().max()),
+                    "abs_err_log_scale_vs_unsharded": abs(c_mine - float(tail[0].item()))})
+        del b, plan
+    dist.barrier()
+    return rec
 
 
 def main():

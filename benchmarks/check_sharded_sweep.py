@@ -40,6 +40,7 @@ for _ in range(10):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     times.append(float(t))
 rec = {"world": world, "workload": f"closed {L}x{L} grid, D = {D}, f64, row-by-row sweep path",
+       "exchange": "one kernel over peer memory (ctn_reshard_peer)" if sw._peer is not None else "merge kernel + NCCL all_to_all_single",
        "segments": len(sw.segments), "exchanges": sum(s.exchange is not None for s in sw.segments),
        "exchanged_MB_per_rank": sw.exchanged_bytes / 1e6,
        "seconds_best": min(times), "seconds_median": sorted(times)[len(times) // 2]}
@@ -58,14 +59,19 @@ def a2a_timed(*a, **k):
     x = ev(); r = orig_a2a(*a, **k); marks.append((-1, "a2a", x, ev())); return r
 def ag_timed(*a, **k):
     x = ev(); r = orig_ag(*a, **k); marks.append((-1, "gather", x, ev())); return r
+orig_rs = parallel.reshard_peer
+def rs_timed(*a, **k):
+    x = ev(); r = orig_rs(*a, **k); marks.append((-1, "reshard", x, ev())); return r
+parallel.reshard_peer = rs_timed
 sw._run_segment = seg_timed; sharded.merge_batch_shards = merge_timed
 dist.all_to_all_single = a2a_timed; dist.all_gather_into_tensor = ag_timed
 e0 = ev(); sw.run(); e1 = ev(); torch.cuda.synchronize()
 sw._run_segment = orig_seg; sharded.merge_batch_shards = orig_merge
-dist.all_to_all_single = orig_a2a; dist.all_gather_into_tensor = orig_ag
+dist.all_to_all_single = orig_a2a; dist.all_gather_into_tensor = orig_ag; parallel.reshard_peer = orig_rs
 tot = lambda kind: sum(a.elapsed_time(b) for _, k, a, b in marks if k == kind)
 rec["timeline_ms"] = {"total": e0.elapsed_time(e1), "segments_compute": tot("compute"), "scale_merges": tot("merge"),
-                      "all_to_all": tot("a2a"), "all_gather": tot("gather"),
+                      "all_to_all": tot("a2a"), "all_gather": tot("gather"), "fused_reshard_kernels": tot("reshard"),
+                      "per_fused_reshard": [round(a.elapsed_time(b), 3) for _, k, a, b in marks if k == "reshard"],
                       "per_segment_compute": [round(a.elapsed_time(b), 3) for _, k, a, b in marks if k == "compute"],
                       "per_all_to_all": [round(a.elapsed_time(b), 3) for _, k, a, b in marks if k == "a2a"]}
 ks = 3 if len(sw.segments) > 3 else 0
@@ -74,6 +80,28 @@ _, _, ms = hit[2].execute_device(hit[1].tensors, out=hit[1].out, timed=True)
 rec["segment_kernels"] = {"segment": ks, "einsum": sw.segments[ks].einstr(), "ms": [round(m, 4) for m in ms],
                           "plan": hit[2].describe().splitlines()}
 
+if sw._peer is not None and "--exchange-bench" in sys.argv:
+    # the exchange kernel alone, back to back on the largest slab (no compute in between: no skew from it)
+    ka = max((k for k, s in enumerate(sw.segments) if s.exchange == "a2a"), key=lambda k: sw._bound[k][1].out.numel())
+    hit = sw._bound[ka]
+    hit[1].run()
+    for _ in range(3):
+        parallel.reshard_peer(hit[1].out, hit[2], sw._peer, 0)
+    sweep = []
+    for ctas in (148, 296, 444, 592, 888, 1184):
+        os.environ["CTN_RESHARD_CTAS"] = str(ctas)
+        parallel.reshard_peer(hit[1].out, hit[2], sw._peer, 0)
+        torch.cuda.synchronize(); dist.barrier()
+        a = ev()
+        for _ in range(20):
+            parallel.reshard_peer(hit[1].out, hit[2], sw._peer, 0)
+        b = ev(); torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 20], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nbytes = hit[1].out.numel() * 8
+        sweep.append({"ctas": ctas, "ms": float(t), "remote_GBps_per_rank": nbytes * (world - 1) / world / float(t) / 1e6})
+    del os.environ["CTN_RESHARD_CTAS"]
+    rec["exchange_alone"] = {"slab_MB": nbytes / 1e6, "remote_MB": nbytes * (world - 1) / world / 1e6, "sweep": sweep}
 if rank == 0:
     plan = engine.get_plan(lst, shapes, np.float64, device=dev.index)
     b = plan.bind(ops)
@@ -96,7 +124,8 @@ if rank == 0:
                     "abs_err_log_scale_vs_oracle": abs(float(c.reshape(-1)[0]) - float(co))})
     print(json.dumps(rec))
     os.makedirs("gpurun_out", exist_ok=True)
-    with open(f"gpurun_out/sharded_sweep_{L}x{L}_D{D}_{world}gpu.json", "w") as f:
+    tag = "" if sw._peer is not None or world == 1 else "_nccl"
+    with open(f"gpurun_out/sharded_sweep_{L}x{L}_D{D}_{world}gpu{tag}.json", "w") as f:
         json.dump(rec, f, indent=1)
     assert rec["max_rel_err_T_vs_unsharded"] < 1e-11 and rec["abs_err_log_scale_vs_unsharded"] < 1e-9
 if world > 1:
