@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(kSkinnyThreads) skinny_dmma_kernel(const StepD
   constexpr int NP = NT8 * 8, LDB = NP + 4;   // LDB = 4 or 12 (mod 16): conflict-free fragment reads
   extern __shared__ double sk_smem[];          // [K_pad][LDB] small operand
   __shared__ int64_t koff_s[kSkinnyMaxK];      // offset of summed index k in the big operand (-1: padding)
+  __shared__ int64_t skof_s[kSkinnyMaxK];      // ... and in the small operand
   __shared__ int64_t ccol_s[64];
+  __shared__ int64_t scol_s[64];               // offset of small-side index n in the small operand
   __shared__ double red[33];
   __shared__ bool last_block;
   const StepDev& s = steps[step_idx];
@@ -225,26 +227,27 @@ __global__ void __launch_bounds__(kSkinnyThreads) skinny_dmma_kernel(const StepD
   const int N = (int)(SWAP ? g.M : g.N);
   const int K = (int)g.K, K_pad = (K + 3) & ~3;
 
+  // the index decompositions (64-bit divisions) are done once per column and once per k, not once per
+  // element of the small operand: the prologue was ~13 us per CTA, a third of a launch on 2.6e5 rows
   for (int n = threadIdx.x; n < NP; n += blockDim.x) {
     int64_t ox = 0, oc = 0;
     if (n < N) sk_offsets(col_modes, n_col_modes, n, !SWAP, ox, oc);
     ccol_s[n] = n < N ? oc : -1;
+    scol_s[n] = ox;
   }
   for (int k = threadIdx.x; k < K_pad; k += blockDim.x) {
-    int64_t ob = -1, dummy;
-    if (k < K) sk_offsets(g.k, g.n_k, k, SWAP, ob, dummy);
+    int64_t ob = -1, os = 0, dummy;
+    if (k < K) {
+      sk_offsets(g.k, g.n_k, k, SWAP, ob, dummy);
+      sk_offsets(g.k, g.n_k, k, !SWAP, os, dummy);
+    }
     koff_s[k] = ob;
+    skof_s[k] = os;
   }
+  __syncthreads();
   for (int e = threadIdx.x; e < K_pad * NP; e += blockDim.x) {
     const int k = e / NP, n = e - k * NP;
-    double v = 0.0;
-    if (n < N && k < K) {
-      int64_t on, ok, dummy;
-      sk_offsets(col_modes, n_col_modes, n, !SWAP, on, dummy);
-      sk_offsets(g.k, g.n_k, k, !SWAP, ok, dummy);
-      v = __ldg(small_g + on + ok);
-    }
-    sk_smem[k * LDB + n] = v;
+    sk_smem[k * LDB + n] = (n < N && k < K) ? __ldg(small_g + scol_s[n] + skof_s[k]) : 0.0;
   }
   __syncthreads();
 
@@ -333,11 +336,17 @@ static cudaError_t launch_dmma(const ExecCtx& c, const Launch& l, int64_t rows, 
   const int np = nt8 * 8, ldb = np + 4, k_pad = (K + 3) & ~3;
   const size_t smem = (size_t)k_pad * ldb * sizeof(double);
   const int64_t per_cta = (kSkinnyThreads / 32) * 32;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + per_cta - 1) / per_cta,
-                                                               std::min<int64_t>((int64_t)p.sm_count * 2, kMaxPartials)));
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
     if (e != cudaSuccess) return e;
+    // one resident wave: a CTA that waits for an SM would run the prologue (small operand -> shared memory)
+    // a second time on it.  The 64-column kernel holds 222 registers: ONE CTA per SM, not the two assumed before
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSkinnyThreads, smem);
+    if (e != cudaSuccess) return e;
+    const int64_t wave = (int64_t)p.sm_count * std::max(1, std::min(occ, 4));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + per_cta - 1) / per_cta,
+                                                                 std::min<int64_t>(wave, kMaxPartials)));
     kern<<<grid, kSkinnyThreads, smem, c.stream>>>(p.d_steps, p.d_gemms, l.first_step, d);
     return cudaGetLastError();
   };
