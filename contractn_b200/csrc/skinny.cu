@@ -20,6 +20,7 @@ namespace ctn {
 
 constexpr int kSkinnyThreads = 256;
 constexpr int kSkinnyMaxK = 256;
+constexpr int kSkinnyDefaultRtWide = 2;  // 8-row tiles per warp for 40..64 columns: 128 registers, two CTAs per SM (cfg 5: 32.6 -> 29.2 ms against 4 tiles, 222 registers, one CTA per SM)
 constexpr int kSkinnyMaxKN = 4096;  // doubles of shared memory for the small operand
 
 __device__ __forceinline__ void sk_offsets(const GemmMode* modes, int n, int64_t idx, bool use_b, int64_t& ox,
@@ -202,7 +203,9 @@ __device__ __forceinline__ void sk_dmma(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-template <int NT8, bool SWAP>
+// RT = 8-row tiles per warp: 4 (32 rows, 222 registers at 64 columns: one CTA per SM) or 2 (16 rows: two CTAs per
+// SM, twice the warps to hide the latency of the direct global loads of the big operand)
+template <int NT8, bool SWAP, int RT>
 __global__ void __launch_bounds__(kSkinnyThreads) skinny_dmma_kernel(const StepDev* __restrict__ steps,
                                                                      const GemmDev* __restrict__ gemms, int step_idx,
                                                                      DevState d) {
@@ -253,14 +256,15 @@ __global__ void __launch_bounds__(kSkinnyThreads) skinny_dmma_kernel(const StepD
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int frow = lane >> 2, fk = lane & 3;
-  const int64_t rows_per_cta = (kSkinnyThreads / 32) * 32;
+  constexpr int WR = RT * 8;  // rows per warp item
+  const int64_t rows_per_cta = (kSkinnyThreads / 32) * WR;
   double local_abs = 0.0;
-  for (int64_t r0 = (int64_t)blockIdx.x * rows_per_cta + warp * 32; r0 < R; r0 += (int64_t)gridDim.x * rows_per_cta) {
-    const double* arow[4];
-    int64_t crow[4];
-    bool live[4];
+  for (int64_t r0 = (int64_t)blockIdx.x * rows_per_cta + warp * WR; r0 < R; r0 += (int64_t)gridDim.x * rows_per_cta) {
+    const double* arow[RT];
+    int64_t crow[RT];
+    bool live[RT];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < RT; ++t) {
       const int64_t r = r0 + t * 8 + frow;
       live[t] = r < R;
       int64_t oa = 0, oc = 0;
@@ -268,28 +272,28 @@ __global__ void __launch_bounds__(kSkinnyThreads) skinny_dmma_kernel(const StepD
       arow[t] = big + oa;
       crow[t] = oc;
     }
-    double acc[4][NT8][2];
+    double acc[RT][NT8][2];
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < RT; ++t)
 #pragma unroll
       for (int j = 0; j < NT8; ++j) acc[t][j][0] = acc[t][j][1] = 0.0;
 #pragma unroll 4
     for (int ks = 0; ks < K_pad; ks += 4) {
       const int64_t ko = koff_s[ks + fk];
-      double a[4];
+      double a[RT];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) a[t] = (ko >= 0 && live[t]) ? __ldg(arow[t] + ko) : 0.0;
+      for (int t = 0; t < RT; ++t) a[t] = (ko >= 0 && live[t]) ? __ldg(arow[t] + ko) : 0.0;
       const double* brow = sk_smem + (ks + fk) * LDB + frow;
 #pragma unroll
       for (int j = 0; j < NT8; ++j) {
         const double b = brow[j * 8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) sk_dmma(acc[t][j], a[t], b);
+        for (int t = 0; t < RT; ++t) sk_dmma(acc[t][j], a[t], b);
       }
     }
     // C fragment: row = lane/4, columns 2*(lane%4) + {0, 1} of each 8x8 tile
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < RT; ++t) {
       if (!live[t]) continue;
       double* out_row = C + crow[t];
 #pragma unroll
@@ -335,12 +339,15 @@ static cudaError_t launch_dmma(const ExecCtx& c, const Launch& l, int64_t rows, 
   const int nt8 = (cols + 7) / 8;
   const int np = nt8 * 8, ldb = np + 4, k_pad = (K + 3) & ~3;
   const size_t smem = (size_t)k_pad * ldb * sizeof(double);
-  const int64_t per_cta = (kSkinnyThreads / 32) * 32;
+  // CTN_SKINNY_RT (experiment knob): 8-row tiles per warp, 2 or 4
+  static const int rt_env = getenv("CTN_SKINNY_RT") ? atoi(getenv("CTN_SKINNY_RT")) : 0;
+  const int rt = rt_env == 2 || rt_env == 4 ? rt_env : (nt8 >= 5 ? kSkinnyDefaultRtWide : 4);
+  const int64_t per_cta = (kSkinnyThreads / 32) * rt * 8;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
     if (e != cudaSuccess) return e;
     // one resident wave: a CTA that waits for an SM would run the prologue (small operand -> shared memory)
-    // a second time on it.  The 64-column kernel holds 222 registers: ONE CTA per SM, not the two assumed before
+    // a second time on it.  The 64-column kernel with 32 rows per warp holds 222 registers: ONE CTA per SM
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSkinnyThreads, smem);
     if (e != cudaSuccess) return e;
@@ -350,15 +357,27 @@ static cudaError_t launch_dmma(const ExecCtx& c, const Launch& l, int64_t rows, 
     kern<<<grid, kSkinnyThreads, smem, c.stream>>>(p.d_steps, p.d_gemms, l.first_step, d);
     return cudaGetLastError();
   };
+  if (rt == 2) {
+    switch (nt8) {
+      case 1: return launch(skinny_dmma_kernel<1, SWAP, 2>);
+      case 2: return launch(skinny_dmma_kernel<2, SWAP, 2>);
+      case 3: return launch(skinny_dmma_kernel<3, SWAP, 2>);
+      case 4: return launch(skinny_dmma_kernel<4, SWAP, 2>);
+      case 5: return launch(skinny_dmma_kernel<5, SWAP, 2>);
+      case 6: return launch(skinny_dmma_kernel<6, SWAP, 2>);
+      case 7: return launch(skinny_dmma_kernel<7, SWAP, 2>);
+      default: return launch(skinny_dmma_kernel<8, SWAP, 2>);
+    }
+  }
   switch (nt8) {
-    case 1: return launch(skinny_dmma_kernel<1, SWAP>);
-    case 2: return launch(skinny_dmma_kernel<2, SWAP>);
-    case 3: return launch(skinny_dmma_kernel<3, SWAP>);
-    case 4: return launch(skinny_dmma_kernel<4, SWAP>);
-    case 5: return launch(skinny_dmma_kernel<5, SWAP>);
-    case 6: return launch(skinny_dmma_kernel<6, SWAP>);
-    case 7: return launch(skinny_dmma_kernel<7, SWAP>);
-    default: return launch(skinny_dmma_kernel<8, SWAP>);
+    case 1: return launch(skinny_dmma_kernel<1, SWAP, 4>);
+    case 2: return launch(skinny_dmma_kernel<2, SWAP, 4>);
+    case 3: return launch(skinny_dmma_kernel<3, SWAP, 4>);
+    case 4: return launch(skinny_dmma_kernel<4, SWAP, 4>);
+    case 5: return launch(skinny_dmma_kernel<5, SWAP, 4>);
+    case 6: return launch(skinny_dmma_kernel<6, SWAP, 4>);
+    case 7: return launch(skinny_dmma_kernel<7, SWAP, 4>);
+    default: return launch(skinny_dmma_kernel<8, SWAP, 4>);
   }
 }
 
