@@ -234,6 +234,12 @@ class ShardedSweep:
 
     ``contract_fn(einstr, *ops, optimize=path, split_format=True) -> (T, c)`` replaces the device plans
     (CPU tests); with it, tensors live wherever the operands live.
+
+    Limits: extents of the sharded legs must be multiples of the world size (legs that are not are never
+    picked; a network without such a leg runs replicated); the result flags of the segment plans are not
+    read back, so a float32 plan with fused steps that meets a degenerate norm (``CTN_RESULT_DEGENERATE``,
+    see ``engine._run_torch_nograd``) is not re-run in exact-step mode here -- the path this class exists
+    for (float64 grids) has no fused steps.
     """
 
     def __init__(self, einstr, operands, optimize="auto", group=None, min_numel=1 << 16, contract_fn=None):

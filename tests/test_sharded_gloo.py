@@ -82,6 +82,31 @@ def test_segmentation_of_a_grid():
     assert total == planner.path_flops(lst, einstr, shapes)
 
 
+def test_no_divisible_label_stays_replicated():
+    """Bond 3 on 2 ranks: no leg can be split evenly, every segment is replicated (no exchange), the
+    result is still the reference's."""
+    einstr, ops, path = _grid(3, 3)
+    shapes = tuple(o.shape for o in ops)
+    lst = planner.cached_contract_list(einstr, shapes, optimize=path)
+    segs, _, _ = sharded.plan_segments(einstr, shapes, lst, 2, min_numel=1)
+    assert all(s.mode == "repl" and s.exchange is None for s in segs)
+    segs4, _, _ = sharded.plan_segments(einstr, shapes, lst, 4, min_numel=1)   # more ranks than the bond is wide
+    assert all(s.mode == "repl" for s in segs4)
+
+
+def test_chain_input_is_listed_last():
+    """The running tensor is the LAST input of every segment after the first, so the planner's step strings put
+    the big operand first (rows of the GEMM) exactly as in the unsharded sweep."""
+    einstr, ops, path = _grid(4, 4)
+    shapes = tuple(o.shape for o in ops)
+    lst = planner.cached_contract_list(einstr, shapes, optimize=path)
+    segs, n, _ = sharded.plan_segments(einstr, shapes, lst, 2, min_numel=64)
+    for s in segs:
+        if s.chain_in is not None:
+            assert s.inputs[-1] == s.chain_in
+            assert all(p[1] == 0 for p in s.path) and s.path[0][0] == len(s.inputs) - 1
+
+
 def _gloo_case(rank, world, name):
     return _check(name)
 
