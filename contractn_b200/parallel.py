@@ -14,6 +14,10 @@ path shards naturally:
   with a log-sum-exp merge and :func:`merge_slice_sums` all-reduces the
   (mantissa, log-scale) pairs over NCCL/NVLink.
 
+* **boundary-sharded sweep** (``contractn_b200.sharded``) -- the bond-parallel path for SPEED: the running
+  intermediate is sharded over one of its legs and re-sharded by ONE kernel over peer memory
+  (:func:`reshard_peer`); total work stays 1x, where bond slicing multiplies it (it buys memory).
+
 Both merges are exact by the gauge property of the split format (SURVEY.md
 finding 0.4): ``T * exp(c)`` is what is summed / concatenated, the final pair is
 re-canonicalised to ``mean|T| == 1``.  Works on CUDA tensors over NCCL and on

@@ -116,3 +116,10 @@ def test_world2_gloo_matches_oracle(name):
     import functools
 
     assert all(_run(functools.partial(_gloo_case, name=name), world=2))
+
+
+def test_world4_gloo_grid_matches_oracle():
+    """Four ranks, bond 4: every sharded leg is split (4, 1) -- the layout of 8 GPUs on bond 8."""
+    import functools
+
+    assert all(_run(functools.partial(_gloo_case, name="grid4"), world=4))
