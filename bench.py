@@ -495,6 +495,8 @@ def run_multi_gpu_records(world, rank, dev):
     except Exception as exc:
         out["sliced"] = {"error": f"{type(exc).__name__}: {exc}"}
     # ---------------- boundary-sharded sweep (cfg 5, work stays 1x) ----------------
+    engine.clear_plan_cache()   # (the cached slab / sliced plans keep their workspaces: tier L holds 68.7 GB)
+    torch.cuda.empty_cache()
     for L in ((8, 9) if world >= 4 else (8,)):
         key = "sharded_sweep" if L == 8 else f"sharded_sweep_{L}x{L}"
         try:
