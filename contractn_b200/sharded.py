@@ -171,16 +171,16 @@ def plan_segments(einstr, shapes, contraction_list, world, min_numel=1 << 16):
         segments.append(seg)
         return seg.out_id
 
-    def start(t, ids, o, removed):
+    def start(ids, o, removed):
         lab = labels[o]
-        s = pick(lab, removed) if world > 0 and numel(lab) >= min_numel else None
+        s = pick(lab, removed) if numel(lab) >= min_numel else None
         # (a label that is summed by the very next chain step would be re-sharded at once: still correct)
         seg = _Segment("shard", s) if s is not None else _Segment("repl")
         seg.steps.append((ids, o))
         seg.chain, seg.chain_labels = o, lab
         return seg
 
-    for t, (ids, o, removed) in enumerate(steps):
+    for ids, o, removed in steps:
         ids = tuple(ids)
         if pending is not None and pending.chain in ids:
             if pending.mode == "shard":
@@ -200,7 +200,7 @@ def plan_segments(einstr, shapes, contraction_list, world, min_numel=1 << 16):
                 if s is not None:
                     prev = pending.chain
                     close(pending)
-                    pending = start(t, ids, o, removed)
+                    pending = start(ids, o, removed)
                     pending.chain_in = prev
                 else:
                     pending.steps.append((ids, o))
@@ -213,7 +213,7 @@ def plan_segments(einstr, shapes, contraction_list, world, min_numel=1 << 16):
         else:
             if pending is not None:
                 close(pending)
-            pending = start(t, ids, o, removed)
+            pending = start(ids, o, removed)
     out_perm = None
     if pending is not None:
         if pending.mode == "shard":
