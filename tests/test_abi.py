@@ -96,3 +96,30 @@ def test_workspace_reuse_keeps_arena_small():
     lst = planner.contract_path(einstr, *shapes, optimize=path)[1]
     p = engine.Plan(lst, shapes, np.float64, flags=engine.CTN_PLAN_NO_INTERPRETER)
     assert p.workspace_bytes < 4 * 128 * 128 * 8 + (1 << 20)
+
+
+def test_header_constants_match_the_host_side():
+    import re
+
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "ctn_b200.h")).read()
+    for name in ("CTN_PLAN_EXACT_STEPS", "CTN_PLAN_NO_INTERPRETER", "CTN_PLAN_NO_GEMM", "CTN_PLAN_RAW_FINAL"):
+        m = re.search(name + r"\s*=\s*(\d+)", hdr)
+        assert m and int(m.group(1)) == getattr(engine, name), name
+    m = re.search(r"#define\s+CTN_MAILBOX_WORDS\s+(\d+)", hdr)
+    assert m and int(m.group(1)) == engine.CTN_MAILBOX_WORDS
+
+
+def test_raw_final_plan_has_no_finalize_launch_and_reports_its_kappa_slot():
+    """CTN_PLAN_RAW_FINAL (the plans that feed ctn_reshard_peer): same launches minus the finalize pass, and
+    the workspace offset of the pending scale is inside the state block; without the flag the offset is -1."""
+    einstr, shapes = "abcde,dexy->abcxy", [(16, 16, 16, 8, 8), (8, 8, 8, 8)]
+    lst = planner.contract_path(einstr, *shapes)[1]
+    plain = engine.Plan(lst, shapes, np.float64)
+    raw = engine.Plan(lst, shapes, np.float64, flags=engine.CTN_PLAN_RAW_FINAL)
+    assert plain.launch_kinds == ("gemm", "finalize") and raw.launch_kinds == ("gemm",)
+    assert plain.final_kappa_offset == -1
+    assert 0 < raw.final_kappa_offset < raw.workspace_bytes and raw.final_kappa_offset % 8 == 0
+    # a plan whose last launch finalises by itself ignores the flag
+    chain = engine.Plan(planner.contract_path("a,ab,bc->c", (3,), (3, 3), (3, 3))[1], [(3,), (3, 3), (3, 3)],
+                        np.float64, flags=engine.CTN_PLAN_RAW_FINAL)
+    assert chain.launch_kinds == ("interp",) and chain.final_kappa_offset == -1
