@@ -497,7 +497,7 @@ def run_multi_gpu_records(world, rank, dev):
     # ---------------- boundary-sharded sweep (cfg 5, work stays 1x) ----------------
     engine.clear_plan_cache()   # (the cached slab / sliced plans keep their workspaces: tier L holds 68.7 GB)
     torch.cuda.empty_cache()
-    for L in ((8, 9) if world >= 4 else (8,)):
+    for L in ((9, 8) if world >= 4 else (8,)):   # (largest first: the peer-mapped receive arena is allocated once)
         key = "sharded_sweep" if L == 8 else f"sharded_sweep_{L}x{L}"
         try:
             out[key] = sharded_sweep_record(L, 8, world, rank, dev)
